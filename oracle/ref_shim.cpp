@@ -1,0 +1,62 @@
+// ref_shim.cpp -- extern "C" handles onto the UNMODIFIED reference `Wavelets` class (our code, not the
+// reference's): lets python (ctypes) drive /root/reference/src/wt.cu's own public API on the GPU box to
+//   (a) dump golden vectors (tests/golden/make_golden.py), (b) pin the CPU restatement, (c) time the
+//   reference's stock kernels (bench.py --impl reference).
+// Built only by `make -C oracle ref` into oracle/_ref/libpdwt_ref.so together with the reference sources where
+// they lie (nothing is copied into the repo).  TEST INFRASTRUCTURE ONLY.
+#include <cuda_runtime.h>
+#include "wt.h"   // the reference's header, found through -I/root/reference/src
+
+extern "C" {
+
+void* ref_create(float* img, int Nr, int Nc, const char* wname, int levels, int memisonhost, int do_separable,
+                 int do_cycle_spinning, int do_swt, int ndim)
+{
+    return new Wavelets(img, Nr, Nc, wname, levels, memisonhost, do_separable, do_cycle_spinning, do_swt, ndim);
+}
+void ref_destroy(void* w) { delete static_cast<Wavelets*>(w); }
+void ref_forward(void* w) { static_cast<Wavelets*>(w)->forward(); }
+void ref_inverse(void* w) { static_cast<Wavelets*>(w)->inverse(); }
+void ref_soft_threshold(void* w, float beta, int app, int normalize)
+{
+    static_cast<Wavelets*>(w)->soft_threshold(beta, app, normalize);
+}
+void ref_hard_threshold(void* w, float beta, int app, int normalize)
+{
+    static_cast<Wavelets*>(w)->hard_threshold(beta, app, normalize);
+}
+float ref_norm1(void* w) { return static_cast<Wavelets*>(w)->norm1(); }
+float ref_norm2sq(void* w) { return static_cast<Wavelets*>(w)->norm2sq(); }
+int ref_get_image(void* w, float* out) { return static_cast<Wavelets*>(w)->get_image(out); }
+int ref_get_coeff(void* w, float* out, int num) { return static_cast<Wavelets*>(w)->get_coeff(out, num); }
+void ref_set_image(void* w, float* img, int on_device) { static_cast<Wavelets*>(w)->set_image(img, on_device); }
+void ref_set_coeff(void* w, float* c, int num, int on_device) { static_cast<Wavelets*>(w)->set_coeff(c, num, on_device); }
+int ref_nlevels(void* w) { return static_cast<Wavelets*>(w)->winfos.nlevels; }
+int ref_hlen(void* w) { return static_cast<Wavelets*>(w)->winfos.hlen; }
+int ref_ndims(void* w) { return static_cast<Wavelets*>(w)->winfos.ndims; }
+int ref_state(void* w) { return (int)static_cast<Wavelets*>(w)->state; }
+int ref_sync(void) { return (int)cudaDeviceSynchronize(); }
+int ref_last_error(void) { return (int)cudaGetLastError(); }
+
+// fwd+inv timing loop with CUDA events on the legacy default stream the reference launches on.
+// Returns milliseconds for `iters` forward()+inverse() pairs (state is reset by forward()).
+float ref_time_fwd_inv(void* w, int iters)
+{
+    Wavelets* W = static_cast<Wavelets*>(w);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    for (int i = 0; i < iters; i++) {
+        W->forward();
+        W->inverse();
+    }
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
+}
