@@ -1,0 +1,580 @@
+// pdwt_capi.cu -- Layer A of the C ABI (include/pdwt_b200.h): filter handles, the 16 transform drivers,
+// threshold and norm drivers, size helpers.  Host-side level loops only; all arithmetic is in the kernels.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+
+#include <atomic>
+
+#include "pdwt_common.cuh"
+#include "filter_bank.inc"
+
+using namespace pdwt;
+
+struct pdwt_filters {
+    Taps taps;
+    char name[128];
+};
+
+namespace pdwt {
+static thread_local int tl_last_cuda = 0;
+static std::atomic<long long> g_launches{0};
+int note_cuda(cudaError_t e)
+{
+    if (e == cudaSuccess) return PDWT_OK;
+    tl_last_cuda = (int)e;
+    return PDWT_ERR_CUDA;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static bool force_generic()
+{
+    const char* e = getenv("PDWT_FORCE_GENERIC");
+    return e && *e && *e != '0';
+}
+}  // namespace pdwt
+
+extern "C" {
+
+const char* pdwt_version(void) { return "pdwt_b200 0.1 (sm_100a)"; }
+int pdwt_last_cuda_error(void) { return tl_last_cuda; }
+const char* pdwt_last_cuda_error_string(void) { return cudaGetErrorString((cudaError_t)tl_last_cuda); }
+long long pdwt_launch_count(void) { return g_launches.load(); }
+int pdwt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------- filters
+int pdwt_wavelet_count(void) { return PDWT_NUM_BANKS; }
+const char* pdwt_wavelet_name(int i) { return (i >= 0 && i < PDWT_NUM_BANKS) ? pdwt_bank_index[i].name : NULL; }
+
+int pdwt_filters_create(pdwt_filters** out, const char* wname, int do_swt)
+{
+    if (!out || !wname) return PDWT_ERR_ARG;
+    *out = NULL;
+    pdwt_filters* f = (pdwt_filters*)calloc(1, sizeof(pdwt_filters));
+    if (!f) return PDWT_ERR_ALLOC;
+    strncpy(f->name, wname, sizeof(f->name) - 1);
+    // Haar aliases use the dedicated kernels when the transform is decimated (separable.cu:24-28)
+    if (!do_swt && (!strcasecmp(wname, "haar") || !strcasecmp(wname, "db1") || !strcasecmp(wname, "bior1.1") ||
+                    !strcasecmp(wname, "rbior1.1"))) {
+        f->taps.hlen = 2;
+        *out = f;
+        return 2;
+    }
+    for (int b = 0; b < PDWT_NUM_BANKS; b++) {
+        if (strcasecmp(wname, pdwt_bank_index[b].name)) continue;
+        const int n = pdwt_bank_index[b].hlen;
+        const float* p = pdwt_bank_pool + pdwt_bank_index[b].offset;
+        f->taps.hlen = n;
+        memcpy(f->taps.L, p, n * sizeof(float));
+        memcpy(f->taps.H, p + n, n * sizeof(float));
+        memcpy(f->taps.IL, p + 2 * n, n * sizeof(float));
+        memcpy(f->taps.IH, p + 3 * n, n * sizeof(float));
+        *out = f;
+        return n;
+    }
+    free(f);
+    return PDWT_ERR_WAVELET;
+}
+
+int pdwt_filters_create_custom(pdwt_filters** out, int hlen, const float* dec_lo, const float* dec_hi,
+                               const float* rec_lo, const float* rec_hi)
+{
+    if (!out || hlen < 1) return PDWT_ERR_ARG;
+    *out = NULL;
+    if (hlen > PDWT_MAX_FILTER_WIDTH) return PDWT_ERR_FILTER_LEN;
+    pdwt_filters* f = (pdwt_filters*)calloc(1, sizeof(pdwt_filters));
+    if (!f) return PDWT_ERR_ALLOC;
+    f->taps.hlen = hlen;
+    if (dec_lo) memcpy(f->taps.L, dec_lo, hlen * sizeof(float));
+    if (dec_hi) memcpy(f->taps.H, dec_hi, hlen * sizeof(float));
+    if (rec_lo) memcpy(f->taps.IL, rec_lo, hlen * sizeof(float));
+    if (rec_hi) memcpy(f->taps.IH, rec_hi, hlen * sizeof(float));
+    strcpy(f->name, "custom");
+    *out = f;
+    return hlen;
+}
+
+void pdwt_filters_destroy(pdwt_filters* f) { free(f); }
+int pdwt_filters_hlen(const pdwt_filters* f) { return f ? f->taps.hlen : PDWT_ERR_ARG; }
+int pdwt_filters_get(const pdwt_filters* f, float* dec_lo, float* dec_hi, float* rec_lo, float* rec_hi)
+{
+    if (!f) return PDWT_ERR_ARG;
+    const size_t n = f->taps.hlen * sizeof(float);
+    if (dec_lo) memcpy(dec_lo, f->taps.L, n);
+    if (dec_hi) memcpy(dec_hi, f->taps.H, n);
+    if (rec_lo) memcpy(rec_lo, f->taps.IL, n);
+    if (rec_hi) memcpy(rec_hi, f->taps.IH, n);
+    return f->taps.hlen;
+}
+
+// ---------------------------------------------------------------------------------------------- size helpers
+int pdwt_div2(int n) { return half_up(n); }
+int pdwt_num_coeffs(pdwt_w_info w) { return (w.ndims == 2 ? 3 : 1) * w.nlevels + 1; }
+
+int pdwt_coeff_dims(pdwt_w_info w, int num, int* nr, int* nc)  // wt.cu:481-504
+{
+    if (num < 0 || num >= pdwt_num_coeffs(w)) return PDWT_ERR_ARG;
+    const int scale = (num == 0) ? w.nlevels : (w.ndims == 2 ? (num - 1) / 3 + 1 : num);
+    int r = w.Nr, c = w.Nc;
+    if (!w.do_swt)
+        for (int i = 0; i < scale; i++) {
+            if (w.ndims == 2) r = half_up(r);
+            c = half_up(c);
+        }
+    if (nr) *nr = r;
+    if (nc) *nc = c;
+    return PDWT_OK;
+}
+
+size_t pdwt_coeff_alloc_elems(pdwt_w_info w, int num)  // common.cu:400-445
+{
+    int r, c;
+    if (num == 0) {  // level-1 sized (full size for the SWT): it doubles as scratch for the inverse
+        r = (w.do_swt || w.ndims == 1) ? w.Nr : half_up(w.Nr);
+        c = w.do_swt ? w.Nc : half_up(w.Nc);
+        return (size_t)r * c;
+    }
+    if (pdwt_coeff_dims(w, num, &r, &c) != PDWT_OK) return 0;
+    return (size_t)r * c;
+}
+
+int pdwt_max_level(int Nr, int Nc, int ndims, int hlen)  // wt.cu:156-159, utils.cu:14-20
+{
+    if (hlen < 2) return 0;
+    int N = (ndims == 2) ? (Nr < Nc ? Nr : Nc) : Nc;
+    int i = N / (hlen - 1), l = 0;
+    while (i >>= 1) ++l;
+    return l;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- driver guts
+namespace {
+
+struct Ctx {
+    const Taps& t;
+    float* img;
+    float** c;
+    float* tmp;
+    pdwt_w_info w;
+    int batch;
+    cudaStream_t s;
+    size_t s_img, s_tmp;
+    Plane2 image() const { return Plane2{img, s_img}; }
+    Plane2 scratch(size_t off = 0) const { return Plane2{tmp + off, s_tmp}; }
+    Plane2 coeff(int k) const { return Plane2{c[k], pdwt_coeff_alloc_elems(w, k)}; }
+};
+
+#define TRY(x)                 \
+    do {                       \
+        int rc__ = (x);        \
+        if (rc__ < 0) return rc__; \
+    } while (0)
+
+int check_args(const pdwt_filters* f, float* d_image, float** d_coeffs, float* d_tmp, pdwt_w_info w, int batch,
+               bool need_filters)
+{
+    if ((need_filters && !f) || !d_image || !d_coeffs || !d_tmp) return PDWT_ERR_ARG;
+    if (w.Nr < 1 || w.Nc < 1 || w.nlevels < 1 || batch < 1 || batch > 65535) return PDWT_ERR_ARG;
+    if (w.ndims != 1 && w.ndims != 2) return PDWT_ERR_ARG;
+    if (need_filters && (f->taps.hlen < 1 || f->taps.hlen > PDWT_MAX_FILTER_WIDTH)) return PDWT_ERR_ARG;
+    return PDWT_OK;
+}
+
+// Where the approximation of level l (0-based, l < L-1 intermediate) lives when no D2D fix-up copy is wanted:
+// the LAST level must land in d_coeffs[0], earlier ones alternate with d_tmp.
+inline bool lands_in_c0(int L, int l) { return ((L - 1 - l) & 1) == 0; }
+
+// ---- separable 2-D DWT --------------------------------------------------------------------------------------
+int fwd_sep_2d(const Ctx& x)
+{
+    const int L = x.w.nlevels;
+    int Nr = x.w.Nr, Nc = x.w.Nc;
+    if (fused_supports_hlen(x.t.hlen) && !force_generic()) {
+        Plane2 cur = x.image();
+        for (int l = 0; l < L; l++) {
+            Plane2 dstA = lands_in_c0(L, l) ? x.coeff(0) : x.scratch();
+            TRY(f_dwt2_fwd_level(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
+                                 x.batch, x.s));
+            cur = dstA;
+            Nr = half_up(Nr);
+            Nc = half_up(Nc);
+        }
+        return PDWT_OK;
+    }
+    // generic two-pass scheme with the reference's buffer plan (separable.cu:179-209)
+    Plane2 t1 = x.scratch(), t2 = x.scratch((size_t)x.w.Nr * half_up(x.w.Nc));
+    for (int l = 0; l < L; l++) {
+        Plane2 src = l ? x.coeff(0) : x.image();
+        TRY(g_fwd_rows(x.t, src, t1, t2, Nr, Nc, x.batch, x.s));
+        TRY(g_fwd_cols(x.t, t1, t2, x.coeff(0), x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr,
+                       half_up(Nc), x.batch, x.s));
+        Nr = half_up(Nr);
+        Nc = half_up(Nc);
+    }
+    return PDWT_OK;
+}
+
+int inv_sep_2d(const Ctx& x)
+{
+    const int L = x.w.nlevels;
+    if (fused_supports_hlen(x.t.hlen) && !force_generic()) {
+        Plane2 cur = x.coeff(0);
+        bool cur_is_c0 = true;
+        for (int l = L - 1; l >= 0; l--) {
+            const int Mr = level_size(x.w.Nr, l, 0), Mc = level_size(x.w.Nc, l, 0);
+            Plane2 dst = (l == 0) ? x.image() : (cur_is_c0 ? x.scratch() : x.coeff(0));
+            TRY(f_dwt2_inv_level(x.t, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), dst, half_up(Mr),
+                                 half_up(Mc), Mr, Mc, x.batch, x.s));
+            cur = dst;
+            cur_is_c0 = !cur_is_c0;
+        }
+        return PDWT_OK;
+    }
+    Plane2 t1 = x.scratch(), t2 = x.scratch((size_t)x.w.Nr * half_up(x.w.Nc));  // separable.cu:343-344
+    for (int l = L - 1; l >= 0; l--) {
+        const int Mr = level_size(x.w.Nr, l, 0), Mc = level_size(x.w.Nc, l, 0);
+        const int nr = half_up(Mr), nc = half_up(Mc);
+        TRY(g_inv_cols(x.t, x.coeff(0), x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), t1, t2, nr, nc, Mr,
+                       x.batch, x.s));
+        TRY(g_inv_rows(x.t, t1, t2, l ? x.coeff(0) : x.image(), Mr, nc, Mc, x.batch, x.s));
+    }
+    return PDWT_OK;
+}
+
+// ---- (batched) 1-D: row passes only; A ping-pongs so that the last level lands in d_coeffs[0] ---------------
+int fwd_sep_1d(const Ctx& x, bool swt)
+{
+    const int L = x.w.nlevels;
+    int Nc = x.w.Nc;
+    Plane2 cur = x.image();
+    for (int l = 0; l < L; l++) {
+        Plane2 dstA = lands_in_c0(L, l) ? x.coeff(0) : x.scratch();
+        if (swt)
+            TRY(g_swt_fwd_rows(x.t, cur, dstA, x.coeff(l + 1), x.w.Nr, Nc, l + 1, x.batch, x.s));
+        else {
+            TRY(g_fwd_rows(x.t, cur, dstA, x.coeff(l + 1), x.w.Nr, Nc, x.batch, x.s));
+            Nc = half_up(Nc);
+        }
+        cur = dstA;
+    }
+    return PDWT_OK;
+}
+
+int inv_sep_1d(const Ctx& x, bool swt)
+{
+    const int L = x.w.nlevels;
+    Plane2 cur = x.coeff(0);
+    bool cur_is_c0 = true;
+    for (int l = L - 1; l >= 0; l--) {
+        Plane2 dst = (l == 0) ? x.image() : (cur_is_c0 ? x.scratch() : x.coeff(0));
+        if (swt)
+            TRY(g_swt_inv_rows(x.t, cur, x.coeff(l + 1), dst, x.w.Nr, x.w.Nc, l + 1, x.batch, x.s));
+        else
+            TRY(g_inv_rows(x.t, cur, x.coeff(l + 1), dst, x.w.Nr, level_size(x.w.Nc, l + 1, 0),
+                           level_size(x.w.Nc, l, 0), x.batch, x.s));
+        cur = dst;
+        cur_is_c0 = !cur_is_c0;
+    }
+    return PDWT_OK;
+}
+
+// ---- separable 2-D SWT (reference buffer plan, separable.cu:496-515 / 629-649) -------------------------------
+int fwd_swt_2d(const Ctx& x)
+{
+    const int Nr = x.w.Nr, Nc = x.w.Nc;
+    Plane2 t1 = x.scratch(), t2 = x.scratch((size_t)Nr * Nc);
+    for (int l = 0; l < x.w.nlevels; l++) {
+        TRY(g_swt_fwd_rows(x.t, l ? x.coeff(0) : x.image(), t1, t2, Nr, Nc, l + 1, x.batch, x.s));
+        TRY(g_swt_fwd_cols(x.t, t1, t2, x.coeff(0), x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
+                           l + 1, x.batch, x.s));
+    }
+    return PDWT_OK;
+}
+
+int inv_swt_2d(const Ctx& x)
+{
+    const int Nr = x.w.Nr, Nc = x.w.Nc;
+    Plane2 t1 = x.scratch(), t2 = x.scratch((size_t)Nr * Nc);
+    for (int l = x.w.nlevels - 1; l >= 0; l--) {
+        TRY(g_swt_inv_cols(x.t, x.coeff(0), x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), t1, t2, Nr, Nc,
+                           l + 1, x.batch, x.s));
+        TRY(g_swt_inv_rows(x.t, t1, t2, l ? x.coeff(0) : x.image(), Nr, Nc, l + 1, x.batch, x.s));
+    }
+    return PDWT_OK;
+}
+
+// ---- single-kernel-per-level families: Haar 2-D / 1-D, non-separable DWT / SWT -----------------------------------
+enum Family { HAAR2, HAAR1, NONSEP, NONSEP_SWT };
+
+int fwd_single(const Ctx& x, Family fam)
+{
+    const int L = x.w.nlevels;
+    int Nr = x.w.Nr, Nc = x.w.Nc;
+    Plane2 cur = x.image();
+    for (int l = 0; l < L; l++) {
+        Plane2 dstA = lands_in_c0(L, l) ? x.coeff(0) : x.scratch();
+        switch (fam) {
+            case HAAR2:
+                TRY(g_haar2d_fwd(cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc, x.batch,
+                                 x.s));
+                Nr = half_up(Nr);
+                Nc = half_up(Nc);
+                break;
+            case HAAR1:
+                TRY(g_haar1d_fwd(cur, dstA, x.coeff(l + 1), x.w.Nr, Nc, x.batch, x.s));
+                Nc = half_up(Nc);
+                break;
+            case NONSEP:
+                TRY(g_nonsep_fwd(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
+                                 x.batch, x.s));
+                Nr = half_up(Nr);
+                Nc = half_up(Nc);
+                break;
+            case NONSEP_SWT:
+                TRY(g_nonsep_swt_fwd(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
+                                     l + 1, x.batch, x.s));
+                break;
+        }
+        cur = dstA;
+    }
+    return PDWT_OK;
+}
+
+int inv_single(const Ctx& x, Family fam)
+{
+    const int L = x.w.nlevels;
+    Plane2 cur = x.coeff(0);
+    bool cur_is_c0 = true;
+    for (int l = L - 1; l >= 0; l--) {
+        Plane2 dst = (l == 0) ? x.image() : (cur_is_c0 ? x.scratch() : x.coeff(0));
+        const int Mr = level_size(x.w.Nr, l, 0), Mc = level_size(x.w.Nc, l, 0);
+        switch (fam) {
+            case HAAR2:
+                TRY(g_haar2d_inv(dst, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), half_up(Mr),
+                                 half_up(Mc), Mr, Mc, x.batch, x.s));
+                break;
+            case HAAR1:
+                TRY(g_haar1d_inv(dst, cur, x.coeff(l + 1), x.w.Nr, half_up(Mc), Mc, x.batch, x.s));
+                break;
+            case NONSEP:
+                TRY(g_nonsep_inv(x.t, dst, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), half_up(Mr),
+                                 half_up(Mc), Mr, Mc, x.batch, x.s));
+                break;
+            case NONSEP_SWT:
+                TRY(g_nonsep_swt_inv(x.t, dst, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), x.w.Nr,
+                                     x.w.Nc, l + 1, x.batch, x.s));
+                break;
+        }
+        cur = dst;
+        cur_is_c0 = !cur_is_c0;
+    }
+    return PDWT_OK;
+}
+
+const Taps kNoTaps = {};
+
+}  // namespace
+
+#define MAKE_CTX(need_f)                                                                      \
+    TRY(check_args(f, d_image, d_coeffs, d_tmp, winfos, batch, need_f));                      \
+    Ctx x{(need_f) ? f->taps : kNoTaps, d_image, d_coeffs, d_tmp, winfos, batch, (cudaStream_t)stream, \
+          (size_t)winfos.Nr * winfos.Nc, 2 * (size_t)winfos.Nr * winfos.Nc}
+
+extern "C" {
+
+int pdwt_forward_separable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return fwd_sep_2d(x); }
+int pdwt_forward_separable_1d(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return fwd_sep_1d(x, false); }
+int pdwt_inverse_separable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return inv_sep_2d(x); }
+int pdwt_inverse_separable_1d(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return inv_sep_1d(x, false); }
+int pdwt_forward_swt_separable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return fwd_swt_2d(x); }
+int pdwt_forward_swt_separable_1d(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return fwd_sep_1d(x, true); }
+int pdwt_inverse_swt_separable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return inv_swt_2d(x); }
+int pdwt_inverse_swt_separable_1d(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return inv_sep_1d(x, true); }
+int pdwt_haar_forward2d(PDWT_DRIVER_ARGS) { MAKE_CTX(false); return fwd_single(x, HAAR2); }
+int pdwt_haar_inverse2d(PDWT_DRIVER_ARGS) { MAKE_CTX(false); return inv_single(x, HAAR2); }
+int pdwt_haar_forward1d(PDWT_DRIVER_ARGS) { MAKE_CTX(false); return fwd_single(x, HAAR1); }
+int pdwt_haar_inverse1d(PDWT_DRIVER_ARGS) { MAKE_CTX(false); return inv_single(x, HAAR1); }
+int pdwt_forward_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return fwd_single(x, NONSEP); }
+int pdwt_inverse_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return inv_single(x, NONSEP); }
+int pdwt_forward_swt_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return fwd_single(x, NONSEP_SWT); }
+int pdwt_inverse_swt_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return inv_single(x, NONSEP_SWT); }
+
+// Wavelets::forward dispatch, wt.cu:247-266
+int pdwt_forward(PDWT_DRIVER_ARGS, int do_separable)
+{
+    const bool haar = (winfos.hlen == 2) && !winfos.do_swt;
+    if (winfos.ndims == 1) {
+        if (haar) return pdwt_haar_forward1d(f, d_image, d_coeffs, d_tmp, winfos, batch, stream);
+        return winfos.do_swt ? pdwt_forward_swt_separable_1d(f, d_image, d_coeffs, d_tmp, winfos, batch, stream)
+                             : pdwt_forward_separable_1d(f, d_image, d_coeffs, d_tmp, winfos, batch, stream);
+    }
+    if (winfos.ndims != 2) return PDWT_ERR_ARG;
+    if (haar) return pdwt_haar_forward2d(f, d_image, d_coeffs, d_tmp, winfos, batch, stream);
+    if (do_separable)
+        return winfos.do_swt ? pdwt_forward_swt_separable(f, d_image, d_coeffs, d_tmp, winfos, batch, stream)
+                             : pdwt_forward_separable(f, d_image, d_coeffs, d_tmp, winfos, batch, stream);
+    return winfos.do_swt ? pdwt_forward_swt_nonseparable(f, d_image, d_coeffs, d_tmp, winfos, batch, stream)
+                         : pdwt_forward_nonseparable(f, d_image, d_coeffs, d_tmp, winfos, batch, stream);
+}
+
+// Wavelets::inverse dispatch, wt.cu:283-303
+int pdwt_inverse(PDWT_DRIVER_ARGS, int do_separable)
+{
+    const bool haar = (winfos.hlen == 2) && !winfos.do_swt;
+    if (winfos.ndims == 1) {
+        if (haar) return pdwt_haar_inverse1d(f, d_image, d_coeffs, d_tmp, winfos, batch, stream);
+        return winfos.do_swt ? pdwt_inverse_swt_separable_1d(f, d_image, d_coeffs, d_tmp, winfos, batch, stream)
+                             : pdwt_inverse_separable_1d(f, d_image, d_coeffs, d_tmp, winfos, batch, stream);
+    }
+    if (winfos.ndims != 2) return PDWT_ERR_ARG;
+    if (haar) return pdwt_haar_inverse2d(f, d_image, d_coeffs, d_tmp, winfos, batch, stream);
+    if (do_separable)
+        return winfos.do_swt ? pdwt_inverse_swt_separable(f, d_image, d_coeffs, d_tmp, winfos, batch, stream)
+                             : pdwt_inverse_separable(f, d_image, d_coeffs, d_tmp, winfos, batch, stream);
+    return winfos.do_swt ? pdwt_inverse_swt_nonseparable(f, d_image, d_coeffs, d_tmp, winfos, batch, stream)
+                         : pdwt_inverse_nonseparable(f, d_image, d_coeffs, d_tmp, winfos, batch, stream);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ thresholds and norms
+namespace {
+
+// segment table of every sub-band in the reference's visiting order: details of level 1..L first, A last
+// (wt.cu:404-417).  beta_of(level) < 0 skips nothing; `with_app` adds A_L (logical size).
+int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with_details, bool with_app,
+                  const float* beta_levels, float beta_app, int op /*0 soft,1 hard,2 asum,3 sumsq*/, double* d_sums,
+                  int* nseg_out)
+{
+    SegTable tab;
+    memset(&tab, 0, sizeof tab);
+    int total = 0;
+    auto flush = [&](void) -> int {
+        if (tab.nseg == 0) return 0;
+        int rc;
+        if (op < 2)
+            rc = e_threshold(tab, op, batch, s);
+        else
+            rc = e_reduce(tab, op - 2, batch, d_sums, s);
+        tab.nseg = 0;
+        return rc;
+    };
+    auto push = [&](int k, float beta) -> int {
+        int r, cdim;
+        if (pdwt_coeff_dims(w, k, &r, &cdim) != PDWT_OK) return PDWT_ERR_ARG;
+        if (!c[k]) return PDWT_ERR_ARG;
+        if (op >= 2 && tab.nseg == kMaxSeg) return PDWT_ERR_ARG;  // reductions need one table (sums layout)
+        if (tab.nseg == kMaxSeg) TRY(flush());
+        tab.ptr[tab.nseg] = c[k];
+        tab.n[tab.nseg] = (unsigned long long)r * cdim;
+        tab.stride[tab.nseg] = pdwt_coeff_alloc_elems(w, k);
+        tab.beta[tab.nseg] = beta;
+        tab.nseg++;
+        total++;
+        return 0;
+    };
+    const int per = (w.ndims == 2) ? 3 : 1;
+    if (with_details)
+        for (int l = 0; l < w.nlevels; l++)
+            for (int b = 1; b <= per; b++) TRY(push(per * l + b, beta_levels ? beta_levels[l] : 0.f));
+    if (with_app) TRY(push(0, beta_app));
+    if (nseg_out) *nseg_out = total;
+    return flush();
+}
+
+// w_call_soft_thresh / w_call_hard_thresh, common.cu:219-282
+int threshold_impl(float** c, float beta, pdwt_w_info w, int app, int normalize, int batch, cudaStream_t s, int hard)
+{
+    if (!c || w.nlevels < 1 || w.nlevels > 32 || batch < 1) return PDWT_ERR_ARG;
+    float beta_app = beta;
+    if (app && !hard && normalize > 0) {  // beta2 = beta / sqrt(2)^nlevels (soft only; hard passes beta, common.cu:270)
+        const int half = w.nlevels / 2;
+        beta_app /= (float)(1 << half);
+        if (half * 2 != w.nlevels) beta_app = (float)((double)beta_app / 1.4142135623730951);
+    }
+    float bl[32];
+    for (int l = 0; l < w.nlevels; l++) {
+        if (normalize > 0) beta = (float)((double)beta / 1.4142135623730951);  // common.cu:244 (SQRT_2 is a double)
+        bl[l] = beta;
+    }
+    return launch_tables(c, w, batch, s, true, app != 0, bl, beta_app, hard ? 1 : 0, nullptr, nullptr);
+}
+
+}  // namespace
+
+namespace pdwt {
+// shared with the Wavelets object: reduction with caller-provided scratch (d_sums/h_sums: batch*kMaxSeg doubles)
+int norm_impl(float** c, pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, double* d_sums, double* h_sums)
+{
+    if (!c || !out || w.nlevels < 1 || batch < 1) return PDWT_ERR_ARG;
+    const int nseg = pdwt_num_coeffs(w);
+    if (nseg > kMaxSeg) return PDWT_ERR_ARG;
+    PDWT_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * batch * nseg, s));
+    int pushed = 0;
+    TRY(launch_tables(c, w, batch, s, true, true, nullptr, 0.f, 2 + mode, d_sums, &pushed));
+    PDWT_CUDA(cudaMemcpyAsync(h_sums, d_sums, sizeof(double) * batch * nseg, cudaMemcpyDeviceToHost, s));
+    PDWT_CUDA(cudaStreamSynchronize(s));
+    // host accumulation in float, sub-band by sub-band in the reference's order (wt.cu:373-394, 400-417)
+    for (int p = 0; p < batch; p++) {
+        float res = 0.0f;
+        for (int k = 0; k < nseg; k++) {
+            const double v = h_sums[(size_t)p * nseg + k];
+            if (mode == 0)
+                res += (float)v;
+            else {
+                const float nrm2 = (float)sqrt(v);
+                res += nrm2 * nrm2;
+            }
+        }
+        out[p] = res;
+    }
+    return PDWT_OK;
+}
+}  // namespace pdwt
+
+extern "C" {
+
+int pdwt_call_soft_thresh(float** d_coeffs, float beta, pdwt_w_info winfos, int do_thresh_appcoeffs, int normalize,
+                          int batch, void* stream)
+{
+    return threshold_impl(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, (cudaStream_t)stream, 0);
+}
+int pdwt_call_hard_thresh(float** d_coeffs, float beta, pdwt_w_info winfos, int do_thresh_appcoeffs, int normalize,
+                          int batch, void* stream)
+{
+    return threshold_impl(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, (cudaStream_t)stream, 1);
+}
+
+static int norm_entry(float** d_coeffs, pdwt_w_info w, int batch, float* out, void* stream, int mode)
+{
+    if (batch < 1) return PDWT_ERR_ARG;
+    double *d = nullptr, *h = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)batch * kMaxSeg;
+    PDWT_CUDA(cudaMalloc(&d, bytes));
+    h = (double*)malloc(bytes);
+    int rc = h ? norm_impl(d_coeffs, w, batch, mode, out, (cudaStream_t)stream, d, h) : PDWT_ERR_ALLOC;
+    free(h);
+    cudaFree(d);
+    return rc;
+}
+int pdwt_norm1(float** d_coeffs, pdwt_w_info winfos, int batch, float* out, void* stream)
+{
+    return norm_entry(d_coeffs, winfos, batch, out, stream, 0);
+}
+int pdwt_norm2sq(float** d_coeffs, pdwt_w_info winfos, int batch, float* out, void* stream)
+{
+    return norm_entry(d_coeffs, winfos, batch, out, stream, 1);
+}
+
+}  // extern "C"

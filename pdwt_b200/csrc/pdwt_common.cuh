@@ -1,0 +1,139 @@
+// pdwt_common.cuh -- shared declarations of libpdwt_b200 (internal; the public surface is include/pdwt_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pdwt_b200.h"
+
+namespace pdwt {
+
+// Filter taps travel to every kernel as a launch parameter (constant bank 0) -- the per-instance replacement of the
+// reference's process-global `__constant__ c_kern_L/H/IL/IH` (common.h:28-31).  644 bytes.
+struct Taps {
+    int hlen;
+    float L[PDWT_MAX_FILTER_WIDTH];   // analysis low-pass   (c_kern_L)
+    float H[PDWT_MAX_FILTER_WIDTH];   // analysis high-pass  (c_kern_H)
+    float IL[PDWT_MAX_FILTER_WIDTH];  // synthesis low-pass  (c_kern_IL)
+    float IH[PDWT_MAX_FILTER_WIDTH];  // synthesis high-pass (c_kern_IH)
+};
+
+// ---- index rules (reference lines cited at each use) ------------------------------------
+__host__ __device__ inline int half_up(int n) { return (n + 1) >> 1; }  // w_div2, utils.cu:24-27
+
+// decimating analysis fold incl. the odd-size "repeat last sample" rule, separable.cu:114-121
+__host__ __device__ inline int fold_dec(int i, int N)
+{
+    const int odd = N & 1;
+    if (i < 0) i += N + odd;
+    if (i > N - 1) i = (i == N && odd) ? N - 1 : i - (N + odd);
+    return i;
+}
+// analysis centre, separable.cu:98-107
+__host__ __device__ inline int centre_fwd(int hlen) { return (hlen & 1) ? hlen / 2 : hlen / 2 - 1; }
+
+// synthesis geometry, separable.cu:249-264: taps per polyphase branch, centre, virtual index shift
+struct SynGeom {
+    int taps, c, shift;
+};
+__host__ __device__ inline SynGeom syn_geometry(int hlen)
+{
+    SynGeom s;
+    const int h2 = hlen / 2;
+    s.c = h2 / 2;
+    s.shift = (h2 & 1) ? 0 : 1;
+    s.taps = (h2 & 1) ? 2 * s.c + 1 : 2 * s.c;
+    return s;
+}
+// undecimated fold with a single +-N wrap, separable.cu:423-433 / 575-579
+__host__ __device__ inline int fold_swt(int g, int jf, int c, int N)
+{
+    int i = g + jf - c;
+    if (jf < c - g) i += N;
+    if (jf > N - 1 - g + c) i -= N;
+    return i;
+}
+__host__ __device__ inline int swt_inv_taps(int hlen) { return (hlen & 1) ? 2 * (hlen / 2) + 1 : 2 * (hlen / 2); }
+
+// ---- error plumbing -----------------------------------------------------------------------------------------
+int note_cuda(cudaError_t e);  // records e for pdwt_last_cuda_error(); returns PDWT_OK / PDWT_ERR_CUDA
+void count_launch(int n = 1);
+
+#define PDWT_CUDA(call)                                        \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return ::pdwt::note_cuda(e__); \
+    } while (0)
+#define PDWT_LAUNCH_CHECK()                                      \
+    do {                                                         \
+        ::pdwt::count_launch();                                  \
+        cudaError_t e__ = cudaGetLastError();                    \
+        if (e__ != cudaSuccess) return ::pdwt::note_cuda(e__);   \
+    } while (0)
+
+inline int idiv_up(int a, int b) { return (a + b - 1) / b; }
+
+// level geometry of one plane
+inline int level_size(int N, int l, int do_swt)
+{
+    if (do_swt) return N;
+    for (int i = 0; i < l; i++) N = half_up(N);
+    return N;
+}
+
+// ---- generic (any size, any hlen <= 40) per-pass launchers, pdwt_generic.cu ---------------------------------
+// Each takes plane strides (floats) for the batch dimension (grid.z = plane).
+struct Plane2 {  // a pointer + per-plane stride
+    float* p;
+    size_t stride;
+};
+int g_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int Nc, int batch, cudaStream_t s);
+int g_fwd_cols(const Taps& t, Plane2 t1, Plane2 t2, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+               cudaStream_t s);
+int g_inv_cols(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 t1, Plane2 t2, int n, int Nc, int M,
+               int batch, cudaStream_t s);
+int g_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int n, int M, int batch, cudaStream_t s);
+int g_swt_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int Nc, int level, int batch,
+                   cudaStream_t s);
+int g_swt_fwd_cols(const Taps& t, Plane2 t1, Plane2 t2, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc,
+                   int level, int batch, cudaStream_t s);
+int g_swt_inv_cols(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 t1, Plane2 t2, int Nr, int Nc,
+                   int level, int batch, cudaStream_t s);
+int g_swt_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int Nc, int level, int batch,
+                   cudaStream_t s);
+int g_haar2d_fwd(Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch, cudaStream_t s);
+int g_haar2d_inv(Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int Nr2, int Nc2, int batch,
+                 cudaStream_t s);
+int g_haar1d_fwd(Plane2 img, Plane2 A, Plane2 D, int Nr, int Nc, int batch, cudaStream_t s);
+int g_haar1d_inv(Plane2 img, Plane2 A, Plane2 D, int Nr, int Nc, int Nc2, int batch, cudaStream_t s);
+int g_nonsep_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+                 cudaStream_t s);
+int g_nonsep_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int Nr2, int Nc2,
+                 int batch, cudaStream_t s);
+int g_nonsep_swt_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int level,
+                     int batch, cudaStream_t s);
+int g_nonsep_swt_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int level,
+                     int batch, cudaStream_t s);
+
+// ---- fused fast paths, pdwt_fused.cu: return 1 if they handled the level, 0 if the shape is not covered ---
+int f_dwt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+                     cudaStream_t s);
+int f_dwt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
+                     int batch, cudaStream_t s);
+
+// ---- element-wise + reductions, pdwt_elementwise.cu ----------------------------------------------------------
+constexpr int kMaxSeg = 64;
+struct SegTable {  // list of (sub-band, length, parameter) handled by one launch
+    int nseg;
+    float* ptr[kMaxSeg];
+    unsigned long long n[kMaxSeg];       // floats per plane to process
+    unsigned long long stride[kMaxSeg];  // floats between planes
+    float beta[kMaxSeg];
+};
+int e_threshold(const SegTable& tab, int hard, int batch, cudaStream_t s);
+// sums[plane*nseg + seg] (double, device) += sum |v| (mode 0) or sum v^2 (mode 1)
+int e_reduce(const SegTable& tab, int mode, int batch, double* d_sums, cudaStream_t s);
+
+}  // namespace pdwt
+
+namespace pdwt {
+bool fused_supports_hlen(int hlen);
+}

@@ -1,0 +1,120 @@
+// pdwt_elementwise.cu -- soft / hard threshold and L1 / L2 reductions over a table of sub-bands.
+//
+// The reference launches one 16x16-block kernel per level (common.cu:219-282) and, for the norms, one blocking
+// cuBLAS call per sub-band (wt.cu:370-418).  Here ONE launch covers every sub-band of every plane: grid.y walks
+// the segment table, grid.z the planes, and each thread streams 128-bit vectors (scalar head/tail for unaligned
+// planes).  Pure HBM streaming: 8 B/coefficient for a threshold, 4 B/coefficient for a norm.
+#include "pdwt_common.cuh"
+
+namespace pdwt {
+
+// w_kern_soft_thresh*, common.cu:13-52
+__device__ __forceinline__ float soft1(float v, float beta) { return copysignf(fmaxf(fabsf(v) - beta, 0.0f), v); }
+// w_kern_hard_thresh*, common.cu:57-97 with W_SIGN (common.cu:7): max(sign(|v|-beta), 0) * v  (keeps 0*v = +-0)
+__device__ __forceinline__ float hard1(float v, float beta)
+{
+    const float s = (fabsf(v) - beta > 0.0f) ? 1.0f : -1.0f;
+    return fmaxf(s, 0.0f) * v;
+}
+
+template <int HARD>
+__global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTable tab)
+{
+    const int seg = blockIdx.y;
+    float* p = tab.ptr[seg] + (size_t)blockIdx.z * tab.stride[seg];
+    const size_t n = tab.n[seg];
+    const float beta = tab.beta[seg];
+    // scalar head up to the first 16-byte boundary, vector body, scalar tail
+    size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;
+    if (head > n) head = n;
+    const size_t nvec = (n - head) >> 2;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    float4* pv = reinterpret_cast<float4*>(p + head);
+    for (size_t i = tid; i < nvec; i += nth) {
+        float4 v = pv[i];
+        if (HARD) {
+            v.x = hard1(v.x, beta); v.y = hard1(v.y, beta); v.z = hard1(v.z, beta); v.w = hard1(v.w, beta);
+        } else {
+            v.x = soft1(v.x, beta); v.y = soft1(v.y, beta); v.z = soft1(v.z, beta); v.w = soft1(v.w, beta);
+        }
+        pv[i] = v;
+    }
+    if (tid < head) p[tid] = HARD ? hard1(p[tid], beta) : soft1(p[tid], beta);
+    const size_t tail0 = head + (nvec << 2);
+    if (tail0 + tid < n) p[tail0 + tid] = HARD ? hard1(p[tail0 + tid], beta) : soft1(p[tail0 + tid], beta);
+}
+
+// sum |v| (MODE 0) or sum v^2 (MODE 1): per-thread double accumulation of float4 loads, warp shuffle tree,
+// one shared-memory pass across the 8 warps, one double atomicAdd per block.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ SegTable tab, double* __restrict__ sums)
+{
+    const int seg = blockIdx.y;
+    const float* p = tab.ptr[seg] + (size_t)blockIdx.z * tab.stride[seg];
+    const size_t n = tab.n[seg];
+    size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;
+    if (head > n) head = n;
+    const size_t nvec = (n - head) >> 2;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    const float4* pv = reinterpret_cast<const float4*>(p + head);
+    double acc = 0.0;
+    auto term = [](float v) -> float { return MODE ? v * v : fabsf(v); };
+    for (size_t i = tid; i < nvec; i += nth) {
+        const float4 v = __ldg(pv + i);
+        // the four terms of one vector are added in float (exact enough: 4 terms), the running sum in double
+        acc += (double)((term(v.x) + term(v.y)) + (term(v.z) + term(v.w)));
+    }
+    if (tid < head) acc += (double)term(p[tid]);
+    const size_t tail0 = head + (nvec << 2);
+    if (tail0 + tid < n) acc += (double)term(p[tail0 + tid]);
+
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double warp_sum[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_sum[wid] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        acc = lane < 8 ? warp_sum[lane] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) atomicAdd(&sums[(size_t)blockIdx.z * tab.nseg + seg], acc);
+    }
+}
+
+static int blocks_for(const SegTable& tab)
+{
+    unsigned long long nmax = 0;
+    for (int i = 0; i < tab.nseg; i++) nmax = tab.n[i] > nmax ? tab.n[i] : nmax;
+    // 256 threads x 4 floats x 4 vectors in flight per thread per pass; cap at 8 waves of 148 SMs
+    unsigned long long b = (nmax + 4095) / 4096;
+    if (b < 1) b = 1;
+    if (b > 148 * 8) b = 148 * 8;
+    return (int)b;
+}
+
+int e_threshold(const SegTable& tab, int hard, int batch, cudaStream_t s)
+{
+    if (tab.nseg == 0) return 0;
+    dim3 grid(blocks_for(tab), tab.nseg, batch);
+    if (hard)
+        k_threshold<1><<<grid, 256, 0, s>>>(tab);
+    else
+        k_threshold<0><<<grid, 256, 0, s>>>(tab);
+    PDWT_LAUNCH_CHECK();
+    return 0;
+}
+
+int e_reduce(const SegTable& tab, int mode, int batch, double* d_sums, cudaStream_t s)
+{
+    if (tab.nseg == 0) return 0;
+    dim3 grid(blocks_for(tab), tab.nseg, batch);
+    if (mode)
+        k_reduce<1><<<grid, 256, 0, s>>>(tab, d_sums);
+    else
+        k_reduce<0><<<grid, 256, 0, s>>>(tab, d_sums);
+    PDWT_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace pdwt

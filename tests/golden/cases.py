@@ -45,6 +45,10 @@ CASES = [
     ("nsswt2_db3_24x40",    (24, 40),   "db3",     3, 0, 1, 2),
 ]
 
+# cases that also carry the four thresholded variants (keeps the committed fixtures small)
+THRESH_CASES = {"c1_haar1d_4096", "dwt2_db7_128", "dwt2_db3_33x47", "haar2_33x47", "dwt1_sym4_5x333", "swt2_db2_48x56",
+                "swt1_haar_2x101", "ns2_db2_33x47", "nsswt2_db2_32"}
+
 THRESH = [  # (tag, kind, beta, do_thresh_appcoeffs, normalize)
     ("soft", "soft", 10.0, 0, 0),
     ("softan", "soft", 25.0, 1, 1),

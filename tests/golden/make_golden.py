@@ -17,7 +17,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from cases import CASES, THRESH, make_input  # noqa: E402
+from cases import CASES, THRESH, THRESH_CASES, make_input  # noqa: E402
 
 fp = C.POINTER(C.c_float)
 
@@ -94,7 +94,7 @@ class Ref:
         self.L.ref_set_image(self.h, img.ctypes.data_as(fp), 0)
 
 
-def run_ref_case(L, x, wname, levels, sep, swt, ndim):
+def run_ref_case(L, x, wname, levels, sep, swt, ndim, thresh=True):
     out = {}
     W = Ref(L, x, wname, levels, sep, swt, ndim)
     out["meta"] = np.array([W.nlevels, W.hlen, W.ndims], dtype=np.int32)
@@ -106,7 +106,7 @@ def run_ref_case(L, x, wname, levels, sep, swt, ndim):
     W.L.ref_inverse(W.h)
     out["recon"] = W.image()
     W.close()
-    for tag, kind, beta, app, nrm in THRESH:
+    for tag, kind, beta, app, nrm in (THRESH if thresh else []):
         # fresh object per variant: in non-separable mode the reference's inverse() leaves the INVERSE filters in
         # the shared constant slots (wt.cu:298), so a forward() after an inverse() is wrong there.
         W = Ref(L, x, wname, levels, sep, swt, ndim)
@@ -122,7 +122,7 @@ def run_ref_case(L, x, wname, levels, sep, swt, ndim):
     return out
 
 
-def run_oracle_case(x, wname, levels, sep, swt, ndim):
+def run_oracle_case(x, wname, levels, sep, swt, ndim, thresh=True):
     import oracle
     out = {}
     W = oracle.Wavelets(x, wname, levels, do_separable=sep, do_swt=swt, ndim=ndim)
@@ -134,7 +134,7 @@ def run_oracle_case(x, wname, levels, sep, swt, ndim):
     out["norm2sq"] = np.float32(W.norm2sq(ref_1d_bug=1))
     W.inverse()
     out["recon"] = W.get_image()
-    for tag, kind, beta, app, nrm in THRESH:
+    for tag, kind, beta, app, nrm in (THRESH if thresh else []):
         W.set_image(x)
         W.forward()
         getattr(W, f"{kind}_threshold")(beta, app, nrm)
@@ -166,9 +166,10 @@ def main():
     report = {}
     for name, shape, wname, levels, sep, swt, ndim in CASES:
         x = make_input(name, shape)
-        ref = run_ref_case(L, x, wname, levels, sep, swt, ndim)
+        th = name in THRESH_CASES
+        ref = run_ref_case(L, x, wname, levels, sep, swt, ndim, th)
         err = L.ref_sync()
-        orc = run_oracle_case(x, wname, levels, sep, swt, ndim)
+        orc = run_oracle_case(x, wname, levels, sep, swt, ndim, th)
         rep = compare(ref, orc)
         worst = max(v["err"] for v in rep.values())
         nbit = sum(v["bitexact"] for v in rep.values())
