@@ -1,0 +1,386 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline measurement of pdwt_b200 (BASELINE.json: "Mpixels/s fwd+inv 2D DWT db7 L3 4096^2;
+achieved HBM GB/s vs B200 peak").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c5img]
+
+One "step" = `forward(); inverse();` of ONE `Wavelets` object holding one 4096x4096 float32 image, db7, 3 levels,
+separable (BASELINE.json configs[1]).  Steps rotate over R=4 objects with distinct images and distinct device
+buffers (about 1 GiB touched between two uses of the same object, 8x the 126 MB L2), so no step finds its inputs
+in L2 from the previous one.  Under torchrun (N>1) every rank runs the same per-GPU workload on its own images
+(weak scaling; the path has no data-path collective -- DESIGN.md section 6); the time is the max over ranks.
+
+JSON line (rank 0):
+  value      Mpixels/s, device-resident inputs, CUDA events on the launching stream
+  e2e        same metric through the public API with pinned HOST buffers: set_image (H2D) -> forward -> inverse
+             -> get_image (D2H) inside the timed region
+  roofline   the dominant kernel (per-kernel CUDA-event pairs recorded by the library's profiler in a separate
+             pass over the same steps): algorithmic bytes per launch / average duration vs the measured HBM peak
+  cpu_baseline  the CPU oracle (port of the reference kernels, OpenMP) on this box's host cores, bounded sample
+`--impl reference` times the reference's own implementation: PDWT has no CPU path, its stock CUDA kernels compiled
+unmodified for sm_100 (oracle/_ref/libpdwt_ref.so, built by `make -C oracle ref`) run on the same GPU through the
+reference's own Wavelets class; if that library cannot be loaded, the CPU oracle port is timed instead.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (Nr, Nc, wavelet, levels)
+    "c2": (4096, 4096, "db7", 3),       # BASELINE.json configs[1] -- the configuration the metric is quoted on
+    "c5img": (2048, 2048, "db7", 3),    # one image of configs[4]
+}
+ROTATE = 4
+METRIC = "Mpixels/s fwd+inv 2D DWT db7 L3 4096^2"
+
+
+def seeded_image(shape, seed):
+    return (np.random.default_rng(seed).standard_normal(shape) * 50 + 128).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions run (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=5)
+
+    def summary(self):
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm   # samples taken under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def dist_setup(n_gpus):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def max_over_ranks(ms, world):
+    if world == 1:
+        return ms
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def algorithmic_bytes(tag):
+    """k_fwd2d[R x C] / k_inv2d[R x C]: one level over an R x C plane reads 4*R*C bytes and writes 4*R*C bytes
+    (8 B per pixel of the level, fp32, compulsory traffic only)."""
+    try:
+        dims = tag[tag.index("[") + 1:tag.index("]")].split("x")
+        return 8.0 * int(dims[0]) * int(dims[1])
+    except ValueError:
+        return None
+
+
+# ============================================================================================ our arm
+def run_ours(args):
+    import torch
+    import pdwt_b200
+    from pdwt_b200 import Wavelets
+
+    world, rank, local = dist_setup(args.gpus)
+    Nr, Nc, wname, levels = WORKLOADS[args.workload]
+    npx = Nr * Nc
+    L = pdwt_b200.lib()
+    if L.pdwt_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device -- pdwt_b200 has no CPU fallback")
+
+    imgs = [seeded_image((Nr, Nc), 1000 * rank + i) for i in range(ROTATE)]
+    Ws = [Wavelets(torch.from_numpy(im).cuda(), wname, levels) for im in imgs]
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        W = Ws[i % ROTATE]
+        W.forward()
+        W.inverse()
+
+    for i in range(args.warmup):
+        step(i)
+    # parity spot check before anything is timed: perfect reconstruction of the rotating images
+    rec = Ws[(args.warmup - 1) % ROTATE].get_image() if args.warmup else None
+    if rec is not None:
+        ref = imgs[(args.warmup - 1) % ROTATE]
+        err = float(np.abs(rec - ref).max() / np.abs(ref).max())
+        if not err < 1e-5:
+            raise SystemExit(f"bench.py: fwd+inv does not reconstruct the image (err {err:.3e})")
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = L.pdwt_launch_count()
+    with ClockSampler(local) as clk:
+        barrier(world)
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+        barrier(world)
+        ms_dev = max_over_ranks(e0.elapsed_time(e1), world)
+        launches = L.pdwt_launch_count() - launches0
+
+        # ---- end to end through the public API with pinned host buffers
+        h_in = [torch.from_numpy(im).pin_memory() for im in imgs]
+        h_out = torch.empty((Nr, Nc), dtype=torch.float32).pin_memory()
+        out_np = h_out.numpy()
+
+        def e2e_step(i):
+            W = Ws[i % ROTATE]
+            W.set_image(h_in[i % ROTATE].numpy())      # H2D (pinned), wt.cu:427
+            W.forward()
+            W.inverse()
+            W.get_image(out_np)                        # D2H (pinned), wt.cu:421
+
+        for i in range(max(1, args.warmup)):
+            e2e_step(i)
+        barrier(world)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(i)
+        e1.record(stream)
+        barrier(world)
+        ms_e2e_wall = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 0.0), world)
+    clocks = clk.summary()
+
+    # ---- per-kernel durations (separate pass; the event pairs perturb back-to-back launches slightly)
+    L.pdwt_profile_begin()
+    for i in range(args.steps):
+        step(i)
+    ents = (pdwt_b200.ProfileEntry * 64)()
+    n = L.pdwt_profile_end(ents, 64)
+    kernels = {}
+    for k in range(max(n, 0)):
+        e = ents[k]
+        kernels[e.name.decode()] = {"launches": e.launches, "avg_us": 1e3 * e.ms_total / e.launches,
+                                    "min_us": 1e3 * e.ms_min, "total_ms": e.ms_total}
+    peak, peak_src = peaks()
+    roof = None
+    if kernels:
+        top = max(kernels, key=lambda k: kernels[k]["total_ms"])
+        ab = algorithmic_bytes(top)
+        if ab:
+            ach = ab / (kernels[top]["avg_us"] * 1e-6) / 1e9
+            roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "algorithmic_bytes_per_launch": ab,
+                    "avg_us": round(kernels[top]["avg_us"], 2), "peak_source": peak_src,
+                    "kernel_share_of_step": round(kernels[top]["total_ms"] / sum(v["total_ms"] for v in kernels.values()), 3)}
+            tr = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the ncu capture
+            if os.path.exists(tr):
+                roof["traffic"] = json.load(open(tr)).get(top.split("[")[0])
+
+    value = world * npx * args.steps / (ms_dev * 1e-3) / 1e6
+    e2e_val = world * npx * args.steps / (ms_e2e * 1e-3) / 1e6
+    whole = 16.0 * npx * args.steps / (ms_dev * 1e-3) / 1e9   # algorithmic GB/s of the whole fwd+inv step, per GPU
+
+    out = {
+        "metric": METRIC, "value": round(value, 1), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 5), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {Nr}x{Nc} float32, {wname}, {levels} levels, separable DWT, "
+                               f"forward()+inverse() of one image per step (BASELINE.json configs[1])",
+                   "l2": f"steps rotate over {ROTATE} Wavelets objects with distinct images/buffers (~1 GiB touched "
+                         f"between reuses, > 126 MB L2); no explicit flush",
+                   "per_gpu": "every rank runs this workload on its own images; no data-path collective"},
+        "e2e": {"value": round(e2e_val, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": 4 * npx,
+                "d2h_bytes_per_step": 4 * npx, "ms_per_step": round(ms_e2e / args.steps, 4),
+                "wall_ms_per_step": round(ms_e2e_wall / args.steps, 4),
+                "api": "Wavelets.set_image(pinned host) -> forward -> inverse -> get_image(pinned host)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "step_algorithmic_gbs": {"achieved": round(whole, 1), "frac_of_peak": round(whole / peak, 4),
+                                 "bytes_per_pixel": 16},
+        "kernels": {k: {"launches": v["launches"], "avg_us": round(v["avg_us"], 2)} for k, v in kernels.items()},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_port_baseline(Nr, Nc, wname, levels, iters=3)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def cpu_port_baseline(Nr, Nc, wname, levels, iters):
+    """the CPU oracle (oracle/pdwt_oracle.c, OpenMP) on this box's host cores: `iters` fwd+inv of the same image"""
+    import oracle
+    x = seeded_image((Nr, Nc), 0)
+    O = oracle.Wavelets(x, wname, levels)
+    O.forward(); O.inverse()        # warm-up (page faults, OpenMP pool)
+    t = []
+    for _ in range(iters):
+        O.set_image(x)
+        t0 = time.perf_counter()
+        O.forward(); O.inverse()
+        t.append(time.perf_counter() - t0)
+    s = float(np.median(t))
+    return {"value": round(Nr * Nc / s / 1e6, 1), "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{iters} x (forward+inverse) of one {Nr}x{Nc} image, median; OpenMP over all host cores"}
+
+
+# ====================================================================================== reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Nr, Nc, wname, levels = WORKLOADS[args.workload]
+    npx = Nr * Nc
+    cfg = {"workload": f"{args.workload}: {Nr}x{Nc} float32, {wname}, {levels} levels, separable DWT, "
+                       f"forward()+inverse() of one image per step (BASELINE.json configs[1])"}
+    base = {"impl": "reference", "metric": METRIC, "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg}
+    so = os.path.join(ROOT, "oracle", "_ref", "libpdwt_ref.so")
+    R = None
+    try:
+        import torch
+        R = C.CDLL(so) if torch.cuda.is_available() else None
+        if R is not None:
+            torch.cuda.set_device(0)
+    except OSError:
+        R = None
+    if R is None:
+        # the reference's CUDA build is not usable here: time the CPU port of its kernels instead
+        cb = cpu_port_baseline(Nr, Nc, wname, levels, iters=max(1, min(args.steps, 5)))
+        base.update({"value": cb["value"], "ms_per_step": round(npx / cb["value"] / 1e3, 3), "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(base), flush=True)
+        return
+    fp = C.POINTER(C.c_float)
+    R.ref_create.restype = C.c_void_p
+    R.ref_create.argtypes = [fp, C.c_int, C.c_int, C.c_char_p] + [C.c_int] * 6
+    R.ref_destroy.argtypes = [C.c_void_p]
+    R.ref_time_rotating.restype = C.c_float
+    R.ref_time_rotating.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
+    R.ref_time_e2e.restype = C.c_float
+    R.ref_time_e2e.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.POINTER(fp), fp]
+    R.ref_get_image.argtypes = [C.c_void_p, fp]
+    import torch
+    imgs = [seeded_image((Nr, Nc), i) for i in range(ROTATE)]
+    hs = (C.c_void_p * ROTATE)(*[R.ref_create(im.ctypes.data_as(fp), Nr, Nc, wname.encode(), levels, 1, 1, 0, 0, 2)
+                                 for im in imgs])
+    with ClockSampler(0) as clk:
+        R.ref_time_rotating(hs, ROTATE, 0, args.warmup)
+        ms = R.ref_time_rotating(hs, ROTATE, args.warmup, args.steps)
+        h_in = [torch.from_numpy(im).pin_memory() for im in imgs]
+        h_out = torch.empty((Nr, Nc), dtype=torch.float32).pin_memory()
+        ins = (fp * ROTATE)(*[C.cast(t.data_ptr(), fp) for t in h_in])
+        outp = C.cast(h_out.data_ptr(), fp)
+        R.ref_time_e2e(hs, ROTATE, 0, max(1, args.warmup), ins, outp)
+        ms_e2e = R.ref_time_e2e(hs, ROTATE, args.warmup, args.steps, ins, outp)
+    rec = h_out.numpy()
+    src = imgs[(args.warmup + args.steps - 1) % ROTATE]
+    err = float(np.abs(rec - src).max() / np.abs(src).max())
+    for h in hs:
+        R.ref_destroy(h)
+    v = npx * args.steps / (ms * 1e-3) / 1e6
+    ve = npx * args.steps / (ms_e2e * 1e-3) / 1e6
+    base.update({
+        "value": round(v, 1), "ms_per_step": round(ms / args.steps, 5),
+        "e2e": {"value": round(ve, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": 4 * npx, "d2h_bytes_per_step": 4 * npx,
+                "ms_per_step": round(ms_e2e / args.steps, 4),
+                "api": "reference Wavelets::set_image(host) -> forward -> inverse -> get_image(host)"},
+        "cpu_baseline": {"value": round(v, 1), "unit": "Mpixels/s", "cores": 0, "kind": "reference",
+                         "sample": "PDWT has no CPU implementation: this is its stock CUDA code (unmodified sources, "
+                                   "nvcc -arch=sm_100, oracle/_ref/libpdwt_ref.so) on the same B200 through the "
+                                   "reference's own Wavelets class; every step, rotating over 4 objects"},
+        "clocks": clk.summary(), "reconstruction_err": err,
+        "config": dict(cfg, l2=f"steps rotate over {ROTATE} reference Wavelets objects"),
+    })
+    print(json.dumps(base), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

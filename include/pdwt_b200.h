@@ -180,6 +180,21 @@ intptr_t pdwt_wavelets_tmp_int_ptr(const pdwt_wavelets* w);
 long long pdwt_wavelets_launch_count(const pdwt_wavelets* w);
 long long pdwt_launch_count(void);     /* process-wide */
 
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Per-kernel timing (measurement aid, no counterpart in the reference).  Between _begin and _end every kernel
+ * launch of this library is bracketed by a CUDA-event pair on the stream it is launched on; _end synchronises,
+ * aggregates by kernel tag (first-seen order) and returns the number of distinct tags (entries beyond
+ * max_entries are dropped).  Process-wide; not meant to be left on in production.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct pdwt_profile_entry {
+    char name[64];
+    int launches;
+    double ms_total, ms_min, ms_max;
+} pdwt_profile_entry;
+int pdwt_profile_begin(void);
+int pdwt_profile_end(pdwt_profile_entry* out, int max_entries);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,4 +59,52 @@ float ref_time_fwd_inv(void* w, int iters)
     cudaEventDestroy(e1);
     return ms;
 }
+
+// `iters` steps of forward()+inverse(), step i on object ws[(first+i) % nw] (rotating objects defeat L2 reuse
+// between steps).  CUDA events on the legacy default stream.  Returns milliseconds for all steps.
+float ref_time_rotating(void** ws, int nw, int first, int iters)
+{
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0, 0);
+    for (int i = 0; i < iters; i++) {
+        Wavelets* W = static_cast<Wavelets*>(ws[(first + i) % nw]);
+        W->forward();
+        W->inverse();
+    }
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
+
+// end to end through the reference's public API with host buffers: set_image (H2D) -> forward -> inverse ->
+// get_image (D2H), every step.
+float ref_time_e2e(void** ws, int nw, int first, int iters, float** host_in, float* host_out)
+{
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0, 0);
+    for (int i = 0; i < iters; i++) {
+        Wavelets* W = static_cast<Wavelets*>(ws[(first + i) % nw]);
+        W->set_image(host_in[(first + i) % nw], 0);
+        W->forward();
+        W->inverse();
+        W->get_image(host_out);
+    }
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
 }

@@ -38,6 +38,11 @@ class WInfo(C.Structure):  # struct w_info, utils.h:9-19
     _fields_ = [(n, C.c_int) for n in ("ndims", "Nr", "Nc", "nlevels", "do_swt", "hlen")]
 
 
+class ProfileEntry(C.Structure):  # pdwt_profile_entry, include/pdwt_b200.h
+    _fields_ = [("name", C.c_char * 64), ("launches", C.c_int), ("ms_total", C.c_double), ("ms_min", C.c_double),
+                ("ms_max", C.c_double)]
+
+
 def build(force: bool = False) -> str:
     from .build import build as _b
     return _b(force=force)
@@ -113,6 +118,7 @@ def lib() -> C.CDLL:
     L.pdwt_wavelets_coeff_int_ptr.restype = C.c_ssize_t
     L.pdwt_wavelets_launch_count.argtypes = [vp]
     L.pdwt_wavelets_launch_count.restype = C.c_longlong
+    L.pdwt_profile_end.argtypes = [C.POINTER(ProfileEntry), ci]
     _lib = L
     return L
 

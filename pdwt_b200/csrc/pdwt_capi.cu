@@ -7,6 +7,10 @@
 #include <strings.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "pdwt_common.cuh"
 #include "filter_bank.inc"
@@ -28,6 +32,39 @@ int note_cuda(cudaError_t e)
     return PDWT_ERR_CUDA;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// ---- per-kernel profiler -------------------------------------------------------------------------------------
+struct ProfRec {
+    const char* tag;
+    cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<bool> g_prof_on{false};
+bool profiling_on() { return g_prof_on.load(std::memory_order_relaxed); }
+void prof_open(const char*, cudaStream_t s, void** ev0)
+{
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    *ev0 = (void*)e;
+}
+void prof_close(const char* tag, cudaStream_t s, void* ev0)
+{
+    cudaEvent_t e1;
+    if (cudaEventCreate(&e1) != cudaSuccess) return;
+    cudaEventRecord(e1, s);
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    g_prof.push_back(ProfRec{tag, (cudaEvent_t)ev0, e1});
+}
+const char* prof_tag(const char* base, int rows, int cols)
+{
+    if (!profiling_on()) return base;
+    static std::map<std::string, std::string> interned;  // node-based: c_str() stays valid
+    char buf[96];
+    snprintf(buf, sizeof buf, "%s[%dx%d]", base, rows, cols);
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    return interned.emplace(buf, buf).first->second.c_str();
+}
 static bool force_generic()
 {
     const char* e = getenv("PDWT_FORCE_GENERIC");
@@ -47,6 +84,56 @@ int pdwt_device_count(void)
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
         cudaGetLastError();
         return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ profiler
+int pdwt_profile_begin(void)
+{
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    for (auto& r : g_prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    g_prof_on.store(true);
+    return PDWT_OK;
+}
+int pdwt_profile_end(pdwt_profile_entry* out, int max_entries)
+{
+    g_prof_on.store(false);
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    std::map<std::string, pdwt_profile_entry> agg;
+    std::vector<std::string> order;
+    int rc = PDWT_OK;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(r.e1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (e != cudaSuccess) rc = note_cuda(e);
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+        auto it = agg.find(r.tag);
+        if (it == agg.end()) {
+            pdwt_profile_entry z;
+            memset(&z, 0, sizeof z);
+            strncpy(z.name, r.tag, sizeof(z.name) - 1);
+            z.ms_min = 1e30;
+            it = agg.emplace(r.tag, z).first;
+            order.push_back(r.tag);
+        }
+        it->second.launches++;
+        it->second.ms_total += ms;
+        if (ms < it->second.ms_min) it->second.ms_min = ms;
+        if (ms > it->second.ms_max) it->second.ms_max = ms;
+    }
+    g_prof.clear();
+    if (rc < 0) return rc;
+    int n = 0;
+    for (auto& k : order) {
+        if (out && n < max_entries) out[n] = agg[k];
+        n++;
     }
     return n;
 }

@@ -69,6 +69,27 @@ void count_launch(int n = 1);
         if (e__ != cudaSuccess) return ::pdwt::note_cuda(e__);   \
     } while (0)
 
+// ---- optional per-kernel timing (pdwt_profile_begin/_end): a CUDA-event pair around every launch made inside the
+// scope, on the stream the kernel is launched on.  Costs nothing when profiling is off.
+bool profiling_on();
+void prof_open(const char* tag, cudaStream_t s, void** ev0);
+void prof_close(const char* tag, cudaStream_t s, void* ev0);
+struct ProfScope {
+    const char* tag;
+    cudaStream_t s;
+    void* ev0;
+    ProfScope(const char* t, cudaStream_t st) : tag(t), s(st), ev0(nullptr)
+    {
+        if (profiling_on()) prof_open(tag, s, &ev0);
+    }
+    ~ProfScope()
+    {
+        if (ev0) prof_close(tag, s, ev0);
+    }
+};
+const char* prof_tag(const char* base, int rows, int cols);  // "base[rows x cols]" (interned) while profiling, else base
+#define PDWT_PROF(tag, stream) ::pdwt::ProfScope prof_scope__((tag), (stream))
+
 inline int idiv_up(int a, int b) { return (a + b - 1) / b; }
 
 // level geometry of one plane

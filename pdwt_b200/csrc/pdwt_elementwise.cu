@@ -95,6 +95,7 @@ static int blocks_for(const SegTable& tab)
 
 int e_threshold(const SegTable& tab, int hard, int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     if (tab.nseg == 0) return 0;
     dim3 grid(blocks_for(tab), tab.nseg, batch);
     if (hard)
@@ -107,6 +108,7 @@ int e_threshold(const SegTable& tab, int hard, int batch, cudaStream_t s)
 
 int e_reduce(const SegTable& tab, int mode, int batch, double* d_sums, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     if (tab.nseg == 0) return 0;
     dim3 grid(blocks_for(tab), tab.nseg, batch);
     if (mode)

@@ -341,6 +341,7 @@ static int launch_fwd(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, P
         configured = true;
     }
     dim3 grid(idiv_up(half_up(Nc), TW), idiv_up(half_up(Nr), TH), batch);
+    PDWT_PROF(prof_tag("k_fwd2d", Nr, Nc), s);
     k_fwd2d<HLEN, TW, TH><<<grid, kFusedThreads, K::SMEM, s>>>(t, src.p, src.stride, A.p, A.stride, H.p, V.p, D.p,
                                                                H.stride, Nr, Nc);
     PDWT_LAUNCH_CHECK();
@@ -359,6 +360,7 @@ static int launch_inv(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Pla
         configured = true;
     }
     dim3 grid(idiv_up(nc, TWC), idiv_up(nr, THC), batch);
+    PDWT_PROF(prof_tag("k_inv2d", Mr, Mc), s);
     k_inv2d<HLEN, TWC, THC><<<grid, kFusedThreads, K::SMEM, s>>>(t, A.p, A.stride, H.p, V.p, D.p, H.stride, dst.p,
                                                                  dst.stride, nr, nc, Mr, Mc);
     PDWT_LAUNCH_CHECK();

@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(GX* GY)
 // ---------------------------------------------------------------------------------------------------- launchers
 int g_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int Nc, int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_fwd_rows<<<grid2(half_up(Nc), Nr, batch), kBlock, 0, s>>>(t, img.p, img.stride, lo.p, lo.stride, hi.p, hi.stride,
                                                                 Nr, Nc);
     PDWT_LAUNCH_CHECK();
@@ -420,6 +421,7 @@ int g_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int Nc, 
 int g_fwd_cols(const Taps& t, Plane2 t1, Plane2 t2, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
                cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_fwd_cols<<<grid2(Nc, half_up(Nr), batch), kBlock, 0, s>>>(t, t1.p, t2.p, t1.stride, A.p, H.p, V.p, D.p, A.stride,
                                                                 H.stride, Nr, Nc);
     PDWT_LAUNCH_CHECK();
@@ -428,6 +430,7 @@ int g_fwd_cols(const Taps& t, Plane2 t1, Plane2 t2, Plane2 A, Plane2 H, Plane2 V
 int g_inv_cols(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 t1, Plane2 t2, int n, int Nc, int M,
                int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_inv_cols<<<grid2(Nc, M, batch), kBlock, 0, s>>>(t, A.p, H.p, V.p, D.p, A.stride, H.stride, t1.p, t2.p, t1.stride,
                                                       n, Nc, M);
     PDWT_LAUNCH_CHECK();
@@ -435,6 +438,7 @@ int g_inv_cols(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 t1,
 }
 int g_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int n, int M, int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_inv_rows<<<grid2(M, Nr, batch), kBlock, 0, s>>>(t, t1.p, t1.stride, t2.p, t2.stride, img.p, img.stride, Nr, n, M);
     PDWT_LAUNCH_CHECK();
     return 0;
@@ -442,6 +446,7 @@ int g_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int n, i
 int g_swt_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int Nc, int level, int batch,
                    cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_swt_fwd_rows<<<grid2(Nc, Nr, batch), kBlock, 0, s>>>(t, img.p, img.stride, lo.p, lo.stride, hi.p, hi.stride, Nr,
                                                            Nc, 1 << (level - 1));
     PDWT_LAUNCH_CHECK();
@@ -450,6 +455,7 @@ int g_swt_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int 
 int g_swt_fwd_cols(const Taps& t, Plane2 t1, Plane2 t2, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc,
                    int level, int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_swt_fwd_cols<<<grid2(Nc, Nr, batch), kBlock, 0, s>>>(t, t1.p, t2.p, t1.stride, A.p, H.p, V.p, D.p, A.stride,
                                                            H.stride, Nr, Nc, 1 << (level - 1));
     PDWT_LAUNCH_CHECK();
@@ -458,6 +464,7 @@ int g_swt_fwd_cols(const Taps& t, Plane2 t1, Plane2 t2, Plane2 A, Plane2 H, Plan
 int g_swt_inv_cols(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 t1, Plane2 t2, int Nr, int Nc,
                    int level, int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_swt_inv_cols<<<grid2(Nc, Nr, batch), kBlock, 0, s>>>(t, A.p, H.p, V.p, D.p, A.stride, H.stride, t1.p, t2.p,
                                                            t1.stride, Nr, Nc, 1 << (level - 1));
     PDWT_LAUNCH_CHECK();
@@ -466,6 +473,7 @@ int g_swt_inv_cols(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2
 int g_swt_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int Nc, int level, int batch,
                    cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_swt_inv_rows<<<grid2(Nc, Nr, batch), kBlock, 0, s>>>(t, t1.p, t1.stride, t2.p, t2.stride, img.p, img.stride, Nr,
                                                            Nc, 1 << (level - 1));
     PDWT_LAUNCH_CHECK();
@@ -473,6 +481,7 @@ int g_swt_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int 
 }
 int g_haar2d_fwd(Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_haar2d_fwd<<<grid2(half_up(Nc), half_up(Nr), batch), kBlock, 0, s>>>(img.p, img.stride, A.p, A.stride, H.p, V.p,
                                                                           D.p, H.stride, Nr, Nc);
     PDWT_LAUNCH_CHECK();
@@ -481,6 +490,7 @@ int g_haar2d_fwd(Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int
 int g_haar2d_inv(Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int Nr2, int Nc2, int batch,
                  cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     (void)Nr;
     k_haar2d_inv<<<grid2(Nc2, Nr2, batch), kBlock, 0, s>>>(img.p, img.stride, A.p, A.stride, H.p, V.p, D.p, H.stride,
                                                           Nc, Nr2, Nc2);
@@ -489,6 +499,7 @@ int g_haar2d_inv(Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int
 }
 int g_haar1d_fwd(Plane2 img, Plane2 A, Plane2 D, int Nr, int Nc, int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_haar1d_fwd<<<grid2(half_up(Nc), Nr, batch), kBlock, 0, s>>>(img.p, img.stride, A.p, A.stride, D.p, D.stride, Nr,
                                                                  Nc);
     PDWT_LAUNCH_CHECK();
@@ -496,6 +507,7 @@ int g_haar1d_fwd(Plane2 img, Plane2 A, Plane2 D, int Nr, int Nc, int batch, cuda
 }
 int g_haar1d_inv(Plane2 img, Plane2 A, Plane2 D, int Nr, int Nc, int Nc2, int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_haar1d_inv<<<grid2(Nc2, Nr, batch), kBlock, 0, s>>>(img.p, img.stride, A.p, A.stride, D.p, D.stride, Nr, Nc, Nc2);
     PDWT_LAUNCH_CHECK();
     return 0;
@@ -503,6 +515,7 @@ int g_haar1d_inv(Plane2 img, Plane2 A, Plane2 D, int Nr, int Nc, int Nc2, int ba
 int g_nonsep_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
                  cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_nonsep_fwd<<<grid2(half_up(Nc), half_up(Nr), batch), kBlock, 0, s>>>(t, img.p, img.stride, A.p, A.stride, H.p,
                                                                           V.p, D.p, H.stride, Nr, Nc);
     PDWT_LAUNCH_CHECK();
@@ -511,6 +524,7 @@ int g_nonsep_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2
 int g_nonsep_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int Nr2, int Nc2,
                  int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_nonsep_inv<<<grid2(Nc2, Nr2, batch), kBlock, 0, s>>>(t, img.p, img.stride, A.p, A.stride, H.p, V.p, D.p, H.stride,
                                                           Nr, Nc, Nr2, Nc2);
     PDWT_LAUNCH_CHECK();
@@ -519,6 +533,7 @@ int g_nonsep_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2
 int g_nonsep_swt_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int level,
                      int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_nonsep_swt_fwd<<<grid2(Nc, Nr, batch), kBlock, 0, s>>>(t, img.p, img.stride, A.p, A.stride, H.p, V.p, D.p,
                                                             H.stride, Nr, Nc, 1 << (level - 1));
     PDWT_LAUNCH_CHECK();
@@ -527,6 +542,7 @@ int g_nonsep_swt_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Pl
 int g_nonsep_swt_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int level,
                      int batch, cudaStream_t s)
 {
+    PDWT_PROF(__func__, s);
     k_nonsep_swt_inv<<<grid2(Nc, Nr, batch), kBlock, 0, s>>>(t, img.p, img.stride, A.p, A.stride, H.p, V.p, D.p,
                                                             H.stride, Nr, Nc, 1 << (level - 1));
     PDWT_LAUNCH_CHECK();
