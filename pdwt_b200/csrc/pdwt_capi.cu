@@ -65,10 +65,17 @@ const char* prof_tag(const char* base, int rows, int cols)
     std::lock_guard<std::mutex> g(g_prof_mu);
     return interned.emplace(buf, buf).first->second.c_str();
 }
-static bool force_generic()
+// Kernel family used for the separable 2-D DWT: 2 = warp-streaming FFMA2 kernels, falling back per level to
+// 1 = tile-fused kernels, falling back to 0 = generic two-pass kernels.  PDWT_PATH=stream|fused|generic (or the older
+// PDWT_FORCE_GENERIC=1) caps the choice; the tests run all three against the same golden vectors.
+static int path_cap()
 {
     const char* e = getenv("PDWT_FORCE_GENERIC");
-    return e && *e && *e != '0';
+    if (e && *e && *e != '0') return 0;
+    e = getenv("PDWT_PATH");
+    if (e && !strcmp(e, "generic")) return 0;
+    if (e && !strcmp(e, "fused")) return 1;
+    return 2;
 }
 }  // namespace pdwt
 
@@ -287,12 +294,18 @@ int fwd_sep_2d(const Ctx& x)
 {
     const int L = x.w.nlevels;
     int Nr = x.w.Nr, Nc = x.w.Nc;
-    if (fused_supports_hlen(x.t.hlen) && !force_generic()) {
+    const int cap = path_cap();
+    if (fused_supports_hlen(x.t.hlen) && cap >= 1) {
         Plane2 cur = x.image();
         for (int l = 0; l < L; l++) {
             Plane2 dstA = lands_in_c0(L, l) ? x.coeff(0) : x.scratch();
-            TRY(f_dwt2_fwd_level(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
-                                 x.batch, x.s));
+            int done = 0;
+            if (cap >= 2)
+                TRY(done = s_dwt2_fwd_level(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3),
+                                            Nr, Nc, x.batch, x.s));
+            if (!done)
+                TRY(f_dwt2_fwd_level(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr,
+                                     Nc, x.batch, x.s));
             cur = dstA;
             Nr = half_up(Nr);
             Nc = half_up(Nc);
@@ -315,14 +328,20 @@ int fwd_sep_2d(const Ctx& x)
 int inv_sep_2d(const Ctx& x)
 {
     const int L = x.w.nlevels;
-    if (fused_supports_hlen(x.t.hlen) && !force_generic()) {
+    const int cap = path_cap();
+    if (fused_supports_hlen(x.t.hlen) && cap >= 1) {
         Plane2 cur = x.coeff(0);
         bool cur_is_c0 = true;
         for (int l = L - 1; l >= 0; l--) {
             const int Mr = level_size(x.w.Nr, l, 0), Mc = level_size(x.w.Nc, l, 0);
             Plane2 dst = (l == 0) ? x.image() : (cur_is_c0 ? x.scratch() : x.coeff(0));
-            TRY(f_dwt2_inv_level(x.t, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), dst, half_up(Mr),
-                                 half_up(Mc), Mr, Mc, x.batch, x.s));
+            int done = 0;
+            if (cap >= 2)
+                TRY(done = s_dwt2_inv_level(x.t, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), dst,
+                                            half_up(Mr), half_up(Mc), Mr, Mc, x.batch, x.s));
+            if (!done)
+                TRY(f_dwt2_inv_level(x.t, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), dst,
+                                     half_up(Mr), half_up(Mc), Mr, Mc, x.batch, x.s));
             cur = dst;
             cur_is_c0 = !cur_is_c0;
         }

@@ -140,6 +140,12 @@ int f_dwt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Pl
 int f_dwt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
                      int batch, cudaStream_t s);
 
+// ---- warp-streaming FFMA2 kernels, pdwt_stream.cu: same convention (1 = handled, 0 = shape not covered, < 0 = error)
+int s_dwt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+                     cudaStream_t s);
+int s_dwt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
+                     int batch, cudaStream_t s);
+
 // ---- element-wise + reductions, pdwt_elementwise.cu ----------------------------------------------------------
 constexpr int kMaxSeg = 64;
 struct SegTable {  // list of (sub-band, length, parameter) handled by one launch

@@ -1,0 +1,609 @@
+// pdwt_stream.cu -- warp-streaming kernels of the separable 2-D DWT for sm_100a (the headline path).
+//
+// One WARP is one worker.  It owns a strip of 64 output columns and marches down the rows of a chunk; nothing is
+// shared between warps, so the kernels contain no block-level barrier at all.
+//
+//   forward (one level, reference separable.cu:91-176)
+//     * input rows arrive in a per-warp shared-memory ring filled by the TMA engine (cp.async.bulk, one row piece per
+//       copy, completion on an mbarrier); the periodic extension of separable.cu:114-121 is folded into the copies
+//       (a wrapped row index, and a second copy for the columns that wrap), so the tap loops never test an index;
+//     * row pass: each lane produces (lo, hi) of its 2 output columns with packed FFMA2 -- one multiplicand x
+//       broadcast against the tap pair (L[j], H[j]) held in a uniform register pair, accumulator pair (lo, hi);
+//     * column pass in scatter form: the fresh (lo, hi) pair is multiplied by the scalar taps L[j] / H[j] into the
+//       hlen/2 pending output rows, accumulator pairs (A, V) and (H, D); a rotating register file of hlen/2 slots,
+//       the loop body unrolled over hlen input rows so every register index is static;
+//     * finished rows leave as 64-bit coalesced stores straight from registers.
+//   inverse (one level, reference separable.cu:246-328)
+//     * coefficient rows are read with coalesced 64-bit loads into a register window of hlen/2 (+1) rows, column
+//       synthesis runs on (A, V) / (H, D) pairs against scalar taps, the two branch sums are added last;
+//     * the two synthesised rows (t1, t2) go through a small per-warp shared-memory tile (swizzled, conflict-free)
+//       so that each lane can do the row synthesis of 8 consecutive pixels of one row; 128-bit coalesced stores.
+//
+// Arithmetic contract: every output is the reference's own fmaf chain -- from 0, ascending tap index, row-pass
+// result rounded to fp32 before the column pass, inverse branch sums added last -- so results are bit-identical to
+// the reference CUDA build (fma.rn.f32x2 is two IEEE fp32 FMAs).  FFMA2 halves the issue slots the FP32 pipe needs,
+// which is what lets shared-memory loads, address arithmetic and stores hide behind the FMAs (tools/ubench_fma.cu).
+//
+// Shapes these kernels take: even hlen in [4, 20], even Nr, Nc % 4 == 0, Nc large enough that a strip wraps at
+// most once, 16-byte aligned planes.  Everything else goes to pdwt_fused.cu / pdwt_generic.cu.
+#include <stdlib.h>
+
+#include "pdwt_common.cuh"
+
+namespace pdwt {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// d = a * b + c on both halves, round-to-nearest (SASS FFMA2; broadcast forms are chosen by ptxas)
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// ---- mbarrier + bulk-copy (TMA engine) primitives ------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// non-blocking probe of the same condition: 1 if the phase with this parity has completed
+__device__ __forceinline__ unsigned mbar_test(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// global -> shared::cta, `bytes` multiple of 16, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+constexpr int round4(int n) { return (n + 3) & ~3; }
+
+// One lane of the (converged) warp, chosen by the hardware; ptxas keeps the guarded block uniform, so the bulk copies
+// inside compile to a single UBLKCP each instead of a per-lane loop.
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// ================================================================================================== forward
+// CTA = ONE warp: every quantity derived from blockIdx is provably warp-uniform, which is what lets ptxas keep the
+// filter taps in uniform registers (FFMA2 R, R, UR, R) and the loop control on the uniform datapath.
+template <int HLEN, int NS_ = 8>
+struct FwdGeom {
+    static constexpr int NC = 2;                        // output columns per lane
+    static constexpr int H2 = HLEN / 2;
+    static constexpr int C = H2 - 1;                    // analysis centre (even hlen), separable.cu:103-107
+    static constexpr int AL = round4(C);                // the strip starts AL input columns left of 2*k0 (16-byte aligned)
+    static constexpr int SH = AL - C;                   // first useful column inside the staged strip
+    static constexpr int WO = 32 * NC;                  // output columns per warp
+    static constexpr int WW = round4(SH + 2 * WO + HLEN - 2);  // staged input columns per row
+    static constexpr int NV = (SH + 2 * NC - 2 + HLEN + 3) / 4;  // 16-byte vectors a lane reads per row
+    static constexpr int NS = NS_;                      // ring slots (2 input rows each)
+    static constexpr int SLOT = 2 * WW;                 // floats per slot
+    static constexpr size_t SMEM = (size_t)NS * (SLOT * sizeof(float) + sizeof(u64));
+    static_assert(4 * (NV - 1) + 2 * NC * 31 + 4 <= WW, "lane window exceeds the staged strip");
+};
+
+template <int HLEN>
+struct FwdParams {
+    float2 lh[HLEN];  // (L[hlen-1-j], H[hlen-1-j]): row-pass tap pairs in the reference's accumulation order
+    float ly[HLEN];   // L[hlen-1-j]
+    float hy[HLEN];   // H[hlen-1-j]
+    const float* src;
+    float *A, *Hb, *V, *D;
+    size_t s_src, s_a, s_d;  // plane strides (floats)
+    int Nr, Nc, nr, nc;      // input and output plane sizes
+    int TH;                  // output rows per chunk
+    int ncb, nrc;            // column blocks, row chunks; grid = ncb * nrc * batch work items
+};
+
+// DBG != 0 builds timing experiments only (wrong results): 1 = no arithmetic, 2 = no staging / no barrier waits
+template <int HLEN, int NS_ = 8, int DBG = 0>
+__global__ void __launch_bounds__(32, 12) k_fwd2d_stream(const __grid_constant__ FwdParams<HLEN> p)
+{
+    using G = FwdGeom<HLEN, NS_>;
+    constexpr int H2 = G::H2, NC = G::NC, NS = G::NS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int item = blockIdx.x;
+
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    const unsigned ring_s = smem_u32(ring);
+    const unsigned bar_s = ring_s + NS * G::SLOT * 4;
+
+    const int cb = item % p.ncb, rest = item / p.ncb, rc = rest % p.nrc, plane = rest / p.nrc;
+    const int k0 = cb * G::WO, y0 = rc * p.TH;
+    const int ny = min(p.TH, p.nr - y0);
+    const int npairs = ny + H2 - 1;          // input row pairs this chunk consumes
+    const int xs = 2 * k0 - G::AL;           // first staged input column (multiple of 4, may be < 0)
+    const float* src = p.src + (size_t)plane * p.s_src;
+
+    // column pieces of one staged row: main part, and the part that wraps around the image (periodic extension,
+    // separable.cu:114-121, even sizes); byte counts and offsets are the same for every row
+    const int x_lo = max(xs, 0), x_hi = min(xs + G::WW, p.Nc);
+    const unsigned main_dst = (x_lo - xs) * 4, main_bytes = (x_hi - x_lo) * 4;
+    const int wrap_src = (xs < 0) ? p.Nc + xs : 0;
+    const unsigned wrap_dst = (xs < 0) ? 0 : (p.Nc - xs) * 4;
+    const unsigned wrap_bytes = (xs < 0) ? -xs * 4 : ((xs + G::WW > p.Nc) ? (xs + G::WW - p.Nc) * 4 : 0);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) mbar_init(bar_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+
+    // ---- staging state (all warp-uniform).  Row pieces go through the TMA engine one cp.async.bulk each; source
+    // pointer, ring position and barrier advance incrementally so a refill costs a handful of uniform instructions.
+    int frow = 2 * y0 - G::C;                // next input row to stage; virtual index wrapped once here ...
+    frow += (frow < 0) ? p.Nr : 0;
+    const char* gnext = reinterpret_cast<const char*>(src + (size_t)frow * p.Nc + x_lo);
+    int to_wrap = p.Nr - frow;               // ... and every time this many more rows have been staged
+    const size_t row_bytes = (size_t)p.Nc * 4, plane_bytes = row_bytes * p.Nr;
+    const long long wrap_delta = ((long long)wrap_src - x_lo) * 4;
+    // stage input row pair q into the ring slot at byte offset `soff` (its barrier: `bar`)
+    auto fill = [&](int q, unsigned soff, unsigned bar) {
+        if (DBG == 2) return;
+        if (q < npairs) {
+            if (elect_one()) {
+                mbar_expect_tx(bar, 2 * G::WW * 4);
+                const char* g0 = gnext;
+                const char* g1 = (to_wrap == 1) ? gnext + row_bytes - plane_bytes : gnext + row_bytes;
+                const unsigned dst = ring_s + soff;
+                bulk_g2s(dst + main_dst, g0, main_bytes, bar);
+                bulk_g2s(dst + G::WW * 4 + main_dst, g1, main_bytes, bar);
+                if (wrap_bytes) {
+                    bulk_g2s(dst + wrap_dst, g0 + wrap_delta, wrap_bytes, bar);
+                    bulk_g2s(dst + G::WW * 4 + wrap_dst, g1 + wrap_delta, wrap_bytes, bar);
+                }
+            }
+            gnext += 2 * row_bytes;
+            to_wrap -= 2;
+            if (to_wrap <= 0) {
+                gnext -= plane_bytes;
+                to_wrap += p.Nr;
+            }
+        }
+    };
+#pragma unroll 1
+    for (int q = 0; q < NS; q++) fill(q, q * G::SLOT * 4, bar_s + 8 * q);
+
+    // pending output rows: slot (y mod H2); pairs (A,V) and (H,D) per owned column
+    u64 aLV[H2][NC], aHD[H2][NC];
+#pragma unroll
+    for (int s = 0; s < H2; s++)
+#pragma unroll
+        for (int c = 0; c < NC; c++) aLV[s][c] = aHD[s][c] = 0ull;
+
+    const int kcol = k0 + NC * lane;                 // first output column of this lane
+    const bool col_ok = kcol < p.nc;                 // nc is even, so the pair is in or out as a whole
+    const size_t o0 = (size_t)y0 * p.nc + kcol;
+    float* oA = p.A + (size_t)plane * p.s_a + o0;
+    float* oH = p.Hb + (size_t)plane * p.s_d + o0;
+    float* oV = p.V + (size_t)plane * p.s_d + o0;
+    float* oD = p.D + (size_t)plane * p.s_d + o0;
+    const float* lane_ring = ring + 2 * NC * lane;
+
+    // one input row: row pass on the lane's window, then the column pass scatters the fresh (lo, hi) pair
+    auto row_step = [&](const float (&xv)[G::NV * 4], const int sb, const int r) {
+        if (DBG == 1) {
+            aLV[sb][0] = pack2(xv[0] + xv[G::NV * 4 - 1], xv[5]);
+            return;
+        }
+        // row pass, w_kern_forward_pass1 (separable.cu:91-131): (lo, hi)[c] = sum_j x[2k - C + j] * (L, H)[hlen-1-j]
+        u64 lohi[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            u64 acc = 0ull;
+#pragma unroll
+            for (int j = 0; j < HLEN; j++) {
+                const float x = xv[G::SH + 2 * c + j];
+                acc = ffma2(pack2(x, x), pack2(p.lh[j].x, p.lh[j].y), acc);
+            }
+            lohi[c] = acc;
+        }
+        // column pass, w_kern_forward_pass2 (separable.cu:135-176), scatter form: this input row is tap
+        // j = r + 2*pp of the output row that sits pp pairs back
+#pragma unroll
+        for (int pp = 0; pp < H2; pp++) {
+            const int j = r + 2 * pp;
+            const int sl = (sb - pp + H2) % H2;
+            const u64 kl = pack2(p.ly[j], p.ly[j]), kh = pack2(p.hy[j], p.hy[j]);
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                aLV[sl][c] = ffma2(lohi[c], kl, j == 0 ? 0ull : aLV[sl][c]);
+                aHD[sl][c] = ffma2(lohi[c], kh, j == 0 ? 0ull : aHD[sl][c]);
+            }
+        }
+    };
+    auto load_row = [&](float (&xv)[G::NV * 4], const float* rowp) {
+#pragma unroll
+        for (int i = 0; i < G::NV; i++) {
+            const float4 f = *reinterpret_cast<const float4*>(rowp + 4 * i);
+            xv[4 * i] = f.x; xv[4 * i + 1] = f.y; xv[4 * i + 2] = f.z; xv[4 * i + 3] = f.w;
+        }
+    };
+
+    // Software pipeline over row pairs: while pair q is being computed its successor's barrier is probed (the probe's
+    // latency hides behind the FFMA2s); at the end of the pair the first row of pair q+1 is already pulled into
+    // registers, so a lone warp keeps its FP32 pipe busy without help from other warps.
+    int q = 0;
+    unsigned soff = 0, bar = bar_s, parity = 0;   // ring position of row pair q
+    float xa[G::NV * 4], xb[G::NV * 4];
+    if (DBG != 2) mbar_wait(bar, parity);
+    load_row(xa, lane_ring);
+    for (;;) {
+#pragma unroll
+        for (int sb = 0; sb < H2; sb++) {  // body: H2 row pairs = hlen input rows; all register indices static
+            const float* rowp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(lane_ring) + soff);
+            load_row(xb, rowp + G::WW);
+            // ring position of pair q+1
+            unsigned nsoff = soff + G::SLOT * 4, nbar = bar + 8, nparity = parity;
+            if (nsoff == NS * G::SLOT * 4) {
+                nsoff = 0;
+                nbar = bar_s;
+                nparity ^= 1;
+            }
+            const bool more = q + 1 < npairs;
+            const unsigned ready = (more && DBG != 2) ? mbar_test(nbar, nparity) : 1u;
+            row_step(xa, sb, 0);
+            row_step(xb, sb, 1);
+            // every lane has consumed both rows of this slot: hand it back to the TMA engine
+            __syncwarp();
+            fill(q + NS, soff, bar);
+            // the output row that received its last tap (j = hlen-1) in this pair
+            if (q >= H2 - 1) {
+                const int sl = (sb + 1) % H2;
+                if (col_ok) {
+                    float a0, v0, a1, v1, h0, d0, h1, d1;
+                    unpack2(aLV[sl][0], a0, v0);
+                    unpack2(aLV[sl][1], a1, v1);
+                    unpack2(aHD[sl][0], h0, d0);
+                    unpack2(aHD[sl][1], h1, d1);
+                    *reinterpret_cast<float2*>(oA) = make_float2(a0, a1);
+                    *reinterpret_cast<float2*>(oH) = make_float2(h0, h1);
+                    *reinterpret_cast<float2*>(oV) = make_float2(v0, v1);
+                    *reinterpret_cast<float2*>(oD) = make_float2(d0, d1);
+                }
+                oA += p.nc; oH += p.nc; oV += p.nc; oD += p.nc;
+            }
+            if (!more) return;
+            if (!ready) mbar_wait(nbar, nparity);
+            q++;
+            soff = nsoff;
+            bar = nbar;
+            parity = nparity;
+            load_row(xa, reinterpret_cast<const float*>(reinterpret_cast<const char*>(lane_ring) + soff));
+        }
+    }
+}
+
+template <int HLEN>
+static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+                             cudaStream_t s)
+{
+    using G = FwdGeom<HLEN>;
+    const int nr = Nr / 2, nc = Nc / 2;
+    // shapes the bulk-copy staging can serve (see the file header); 0 = "not handled"
+    if ((Nr & 1) || (Nc & 3) || Nc < G::WW || Nr < HLEN) return 0;
+    if ((((uintptr_t)src.p) & 15) || (src.stride & 3)) return 0;
+    if ((((uintptr_t)A.p | (uintptr_t)H.p | (uintptr_t)V.p | (uintptr_t)D.p) & 7) || (A.stride & 1) || (H.stride & 1))
+        return 0;
+    static bool configured = false;
+    if (!configured) {
+        PDWT_CUDA(cudaFuncSetAttribute(k_fwd2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        configured = true;
+    }
+    FwdParams<HLEN> p;
+    for (int j = 0; j < HLEN; j++) {
+        p.lh[j] = make_float2(t.L[HLEN - 1 - j], t.H[HLEN - 1 - j]);
+        p.ly[j] = t.L[HLEN - 1 - j];
+        p.hy[j] = t.H[HLEN - 1 - j];
+    }
+    p.src = src.p; p.A = A.p; p.Hb = H.p; p.V = V.p; p.D = D.p;
+    p.s_src = src.stride; p.s_a = A.stride; p.s_d = H.stride;
+    p.Nr = Nr; p.Nc = Nc; p.nr = nr; p.nc = nc;
+    p.ncb = idiv_up(nc, G::WO);
+    // chunk height: aim at >= 4 worker warps per SM sub-partition's worth of items (148 SMs x 16 resident warps),
+    // but never below 16 output rows (the vertical halo is hlen-2 input rows per chunk)
+    // chunk height: the largest power of two in [8, 64] that still yields ~1.5 worker warps per SM sub-partition
+    // (148 x 4 of them); the vertical halo costs hlen-2 input rows of row-pass work per chunk
+    int TH = 64;
+    while (TH > 8 && (long long)p.ncb * idiv_up(nr, TH) * batch < 900) TH >>= 1;
+    if (const char* e = getenv("PDWT_TH")) TH = atoi(e) > 0 ? atoi(e) : TH;
+    p.TH = TH;
+    p.nrc = idiv_up(nr, TH);
+    const long long nitems = (long long)p.ncb * p.nrc * batch;
+    if (nitems > 0x7fffffff) return 0;
+    PDWT_PROF(prof_tag("k_fwd2d_stream", Nr, Nc), s);
+#ifdef PDWT_EXPERIMENTS
+    if (HLEN == 14) {
+        const char* e = getenv("PDWT_DBG");
+        const int dbg = e ? atoi(e) : 0;
+        if (dbg == 1) { k_fwd2d_stream<HLEN, 8, 1><<<(unsigned)nitems, 32, G::SMEM, s>>>(p); PDWT_LAUNCH_CHECK(); return 1; }
+        if (dbg == 2) { k_fwd2d_stream<HLEN, 8, 2><<<(unsigned)nitems, 32, G::SMEM, s>>>(p); PDWT_LAUNCH_CHECK(); return 1; }
+        if (dbg == 16) {
+            using G16 = FwdGeom<HLEN, 16>;
+            cudaFuncSetAttribute(k_fwd2d_stream<HLEN, 16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G16::SMEM);
+            k_fwd2d_stream<HLEN, 16, 0><<<(unsigned)nitems, 32, G16::SMEM, s>>>(p); PDWT_LAUNCH_CHECK(); return 1;
+        }
+    }
+#endif
+    k_fwd2d_stream<HLEN><<<(unsigned)nitems, 32, G::SMEM, s>>>(p);
+    PDWT_LAUNCH_CHECK();
+    return 1;
+}
+
+// ================================================================================================== inverse
+// Index rules of the synthesis passes (separable.cu:246-328), per axis, for the output pair
+// (2m, 2m+1):   even output: coefficients m-CC+j,        taps  IL/IH[hlen-1-(2j+1-SHIFT)]
+//               odd  output: coefficients m-CC+SHIFT+j,  taps  IL/IH[hlen-1-(2j+SHIFT)]        j = 0 .. hlen/2-1
+// with CC = (hlen/2)/2 and SHIFT = 1 when hlen/2 is even (the reference's "virtual id for shift").
+template <int HLEN>
+struct InvGeom {
+    static constexpr int H2 = HLEN / 2;
+    static constexpr int CC = H2 / 2;
+    static constexpr int SHIFT = (H2 & 1) ? 0 : 1;
+    static constexpr int WIN = H2 + SHIFT;              // coefficient rows (columns) behind one output pair
+    static constexpr int NSLOT = WIN + 1;               // register window: WIN rows + one row of prefetch
+    static constexpr int ALC = (CC + 1) & ~1;           // the strip starts ALC coefficient columns left of k0 (even)
+    static constexpr int SHC = ALC - CC;
+    static constexpr int NP = (SHC + WIN + 3 + 1) & ~1; // (t1,t2) pairs a row-synthesis lane reads (4 coefficient columns)
+    static constexpr int WOUT = 4 * ((64 - NP) / 4) + 4; // coefficient columns a warp turns into pixels
+    static constexpr int LPR = WOUT / 4;                // row-synthesis lanes per output row (<= 16)
+    static constexpr size_t SMEM = 2 * 2 * 64 * 8;      // double-buffered tile: 2 output rows x 64 (t1,t2) pairs
+    static_assert(LPR <= 16 && WOUT - 4 + NP <= 64, "row-synthesis window exceeds the strip");
+};
+
+template <int HLEN>
+struct InvParams {
+    float il[2][HLEN / 2], ih[2][HLEN / 2];  // [output parity][j]: IL / IH taps in accumulation order
+    float2 lh[2][HLEN / 2];                  // the same as (IL, IH) pairs for the row synthesis
+    const float *A, *Hb, *V, *D;
+    float* dst;
+    size_t s_a, s_d, s_dst;                  // plane strides (floats)
+    int nr, nc, Mr, Mc;                      // coefficient and output plane sizes (Mr = 2 nr, Mc = 2 nc)
+    int TM;                                  // output row PAIRS per chunk
+    int ncb, nrc;
+};
+
+// shared-memory position (in 16-byte chunks) of chunk q of a tile row: XOR swizzle so that both the writers (lane ->
+// chunk lane) and the readers (lane -> chunks 2*lane' + v) are bank-conflict free
+__device__ __forceinline__ int swz(int q) { return q ^ ((q >> 3) & 1); }
+
+template <int HLEN>
+__global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__ InvParams<HLEN> p)
+{
+    using G = InvGeom<HLEN>;
+    constexpr int H2 = G::H2, NSLOT = G::NSLOT, WIN = G::WIN, SHIFT = G::SHIFT;
+    __shared__ __align__(16) float tile[2][2][64 * 2];   // [buffer][output row parity][(t1,t2) x 64]
+    const int lane = threadIdx.x;
+    const int item = blockIdx.x;
+    const int cb = item % p.ncb, rest = item / p.ncb, rc = rest % p.nrc, plane = rest / p.nrc;
+    const int k0 = cb * G::WOUT, m0 = rc * p.TM;
+    const int nm = min(p.TM, p.nr - m0);
+
+    // ---- column synthesis side: this lane owns coefficient columns (col, col+1) of the strip, wrapped periodically
+    int col = k0 - G::ALC + 2 * lane;
+    col += (col < 0) ? p.nc : 0;
+    col -= (col >= p.nc) ? p.nc : 0;
+    const float* pA = p.A + (size_t)plane * p.s_a + col;
+    const float* pH = p.Hb + (size_t)plane * p.s_d + col;
+    const float* pV = p.V + (size_t)plane * p.s_d + col;
+    const float* pD = p.D + (size_t)plane * p.s_d + col;
+    int lrow = m0 - G::CC;                    // next coefficient row to load (wrapped: separable.cu:265-273)
+    lrow += (lrow < 0) ? p.nr : 0;
+    size_t roff = (size_t)lrow * p.nc;
+    int to_wrap = p.nr - lrow;
+
+    u64 wA[NSLOT], wH[NSLOT], wV[NSLOT], wD[NSLOT];  // register window, slot = (row index within the chunk) % NSLOT
+    auto load_row = [&](const int slot) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(pA + roff));
+        const float2 h = __ldg(reinterpret_cast<const float2*>(pH + roff));
+        const float2 v = __ldg(reinterpret_cast<const float2*>(pV + roff));
+        const float2 d = __ldg(reinterpret_cast<const float2*>(pD + roff));
+        wA[slot] = pack2(a.x, a.y);
+        wH[slot] = pack2(h.x, h.y);
+        wV[slot] = pack2(v.x, v.y);
+        wD[slot] = pack2(d.x, d.y);
+        roff += p.nc;
+        if (--to_wrap == 0) {
+            roff = 0;
+            to_wrap = p.nr;
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < NSLOT; i++) wA[i] = wH[i] = wV[i] = wD[i] = 0ull;
+#pragma unroll
+    for (int i = 0; i < WIN; i++) load_row(i);
+
+    // ---- row synthesis side: lanes 0..LPR-1 take the even output row, lanes 16..16+LPR-1 the odd one; each turns 4
+    // coefficient columns into 8 pixels
+    const int g = lane >> 4, lq = lane & 15;
+    const int px0 = 2 * k0 + 8 * lq;
+    const bool row_lane = lq < G::LPR;
+    float* out = p.dst + (size_t)plane * p.s_dst + (size_t)(2 * m0 + g) * p.Mc + px0;
+    const bool st0 = row_lane && px0 + 4 <= p.Mc, st1 = row_lane && px0 + 8 <= p.Mc;
+    int rd_off[G::NP / 2];                    // float offsets of the chunks this lane reads, within one tile row
+#pragma unroll
+    for (int v = 0; v < G::NP / 2; v++) rd_off[v] = 4 * swz((2 * lq + v) & 31);
+    const int wr_off = 4 * swz(lane);
+    int buf = 0;
+
+    int s = 0;
+    for (;;) {
+#pragma unroll
+        for (int sb = 0; sb < NSLOT; sb++) {  // body: NSLOT output row pairs; all register indices static
+            if (s >= nm) return;
+            if (s + 1 < nm) load_row((sb + WIN) % NSLOT);   // prefetch the row the next pair adds
+            // column synthesis, w_kern_inverse_pass1 (separable.cu:246-289): t1 = IL_y(A) + IH_y(H), t2 = IL_y(V) + IH_y(D)
+#pragma unroll
+            for (int par = 0; par < 2; par++) {
+                u64 sa = 0ull, sh = 0ull, sv = 0ull, sd = 0ull;
+#pragma unroll
+                for (int j = 0; j < H2; j++) {
+                    const int sl = (sb + (par ? SHIFT : 0) + j) % NSLOT;
+                    const u64 kl = pack2(p.il[par][j], p.il[par][j]), kh = pack2(p.ih[par][j], p.ih[par][j]);
+                    sa = ffma2(wA[sl], kl, sa);
+                    sh = ffma2(wH[sl], kh, sh);
+                    sv = ffma2(wV[sl], kl, sv);
+                    sd = ffma2(wD[sl], kh, sd);
+                }
+                float t1a, t1b, t2a, t2b;
+                unpack2(fadd2(sa, sh), t1a, t1b);
+                unpack2(fadd2(sv, sd), t2a, t2b);
+                *reinterpret_cast<float4*>(&tile[buf][par][wr_off]) = make_float4(t1a, t2a, t1b, t2b);
+            }
+            __syncwarp();
+            // row synthesis, w_kern_inverse_pass2 (separable.cu:293-328): img = IL_x(t1) + IH_x(t2)
+            if (row_lane) {
+                u64 tw[G::NP];
+#pragma unroll
+                for (int v = 0; v < G::NP / 2; v++) {
+                    const float4 f = *reinterpret_cast<const float4*>(&tile[buf][g][rd_off[v]]);
+                    tw[2 * v] = pack2(f.x, f.y);
+                    tw[2 * v + 1] = pack2(f.z, f.w);
+                }
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int e = k & 1;
+                    const int i0 = (k >> 1) + G::SHC + (e ? SHIFT : 0);
+                    u64 acc = 0ull;
+#pragma unroll
+                    for (int j = 0; j < H2; j++) acc = ffma2(tw[i0 + j], pack2(p.lh[e][j].x, p.lh[e][j].y), acc);
+                    float r1, r2;
+                    unpack2(acc, r1, r2);
+                    o[k] = __fadd_rn(r1, r2);
+                }
+                if (st0) *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+                if (st1) *reinterpret_cast<float4*>(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            out += 2 * (size_t)p.Mc;
+            buf ^= 1;
+            s++;
+        }
+    }
+}
+
+template <int HLEN>
+static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr,
+                             int Mc, int batch, cudaStream_t s)
+{
+    using G = InvGeom<HLEN>;
+    if (Mr != 2 * nr || Mc != 2 * nc || (nc & 1) || nc < 64 || nr < G::WIN) return 0;
+    if ((((uintptr_t)A.p | (uintptr_t)H.p | (uintptr_t)V.p | (uintptr_t)D.p) & 7) || (A.stride & 1) || (H.stride & 1))
+        return 0;
+    if ((((uintptr_t)dst.p) & 15) || (dst.stride & 3)) return 0;
+    InvParams<HLEN> p;
+    for (int par = 0; par < 2; par++) {
+        const int off = par ? G::SHIFT : 1 - G::SHIFT;
+        for (int j = 0; j < HLEN / 2; j++) {
+            p.il[par][j] = t.IL[HLEN - 1 - (2 * j + off)];
+            p.ih[par][j] = t.IH[HLEN - 1 - (2 * j + off)];
+            p.lh[par][j] = make_float2(p.il[par][j], p.ih[par][j]);
+        }
+    }
+    p.A = A.p; p.Hb = H.p; p.V = V.p; p.D = D.p; p.dst = dst.p;
+    p.s_a = A.stride; p.s_d = H.stride; p.s_dst = dst.stride;
+    p.nr = nr; p.nc = nc; p.Mr = Mr; p.Mc = Mc;
+    p.ncb = idiv_up(nc, G::WOUT);
+    // chunk height: a chunk re-reads only WIN-1 coefficient rows, so small chunks are cheap; aim at ~4 waves of 12 warps/SM
+    int TM = 32;
+    while (TM > 4 && (long long)p.ncb * idiv_up(nr, TM) * batch < 148LL * 12 * 2) TM >>= 1;
+    if (const char* e = getenv("PDWT_TM")) TM = atoi(e) > 0 ? atoi(e) : TM;
+    p.TM = TM;
+    p.nrc = idiv_up(nr, TM);
+    const long long nitems = (long long)p.ncb * p.nrc * batch;
+    if (nitems > 0x7fffffff) return 0;
+    PDWT_PROF(prof_tag("k_inv2d_stream", Mr, Mc), s);
+    k_inv2d_stream<HLEN><<<(unsigned)nitems, 32, 0, s>>>(p);
+    PDWT_LAUNCH_CHECK();
+    return 1;
+}
+
+#define PDWT_STREAM_HLEN_SWITCH(fn, ...)            \
+    switch (t.hlen) {                               \
+        case 4: return fn<4>(__VA_ARGS__);          \
+        case 6: return fn<6>(__VA_ARGS__);          \
+        case 8: return fn<8>(__VA_ARGS__);          \
+        case 10: return fn<10>(__VA_ARGS__);        \
+        case 12: return fn<12>(__VA_ARGS__);        \
+        case 14: return fn<14>(__VA_ARGS__);        \
+        case 16: return fn<16>(__VA_ARGS__);        \
+        case 18: return fn<18>(__VA_ARGS__);        \
+        case 20: return fn<20>(__VA_ARGS__);        \
+        default: return 0;                          \
+    }
+
+int s_dwt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+                     cudaStream_t s)
+{
+    PDWT_STREAM_HLEN_SWITCH(launch_fwd_stream, t, src, A, H, V, D, Nr, Nc, batch, s)
+}
+
+int s_dwt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
+                     int batch, cudaStream_t s)
+{
+    PDWT_STREAM_HLEN_SWITCH(launch_inv_stream, t, A, H, V, D, dst, nr, nc, Mr, Mc, batch, s)
+}
+
+}  // namespace pdwt

@@ -25,12 +25,11 @@ def rnd(shape, seed=0):
     return (np.random.default_rng(seed).standard_normal(shape) * 50 + 128).astype(np.float32)
 
 
-@pytest.fixture(params=["fused", "generic"])
+@pytest.fixture(params=["stream", "fused", "generic"])
 def path(request, monkeypatch):
-    if request.param == "generic":
-        monkeypatch.setenv("PDWT_FORCE_GENERIC", "1")
-    else:
-        monkeypatch.delenv("PDWT_FORCE_GENERIC", raising=False)
+    """the three kernel families of the separable 2-D DWT (pdwt_capi.cu path_cap); the others ignore the switch"""
+    monkeypatch.delenv("PDWT_FORCE_GENERIC", raising=False)
+    monkeypatch.setenv("PDWT_PATH", request.param)
     return request.param
 
 
@@ -69,6 +68,10 @@ def test_golden_vectors(case, golden_dir, path):
 
 ORACLE_CASES = [
     # shape, wname, levels, sep, swt, ndim
+    ((1024, 1024), "db7", 3, 1, 0, 2), ((512, 1280), "sym8", 2, 1, 0, 2), ((768, 1028), "db2", 2, 1, 0, 2),
+    ((640, 600), "db3", 2, 1, 0, 2), ((520, 776), "db4", 2, 1, 0, 2), ((512, 520), "db5", 2, 1, 0, 2),
+    ((384, 644), "db6", 2, 1, 0, 2), ((400, 900), "db9", 2, 1, 0, 2), ((448, 704), "coif3", 2, 1, 0, 2),
+    ((330, 1100), "sym7", 2, 1, 0, 2),
     ((512, 512), "db7", 3, 1, 0, 2), ((1024, 768), "db7", 3, 1, 0, 2), ((300, 520), "sym8", 3, 1, 0, 2),
     ((257, 255), "db4", 3, 1, 0, 2), ((130, 66), "db10", 2, 1, 0, 2), ((512, 384), "coif1", 4, 1, 0, 2),
     ((640, 648), "bior4.4", 3, 1, 0, 2), ((200, 200), "db12", 2, 1, 0, 2), ((96, 1000), "db2", 4, 1, 0, 2),
@@ -123,16 +126,17 @@ def test_c2_full_size_properties():
     coeffs = [W.get_coeff(i) for i in range(W.ncoeffs)]
     W.inverse()
     assert nerr(W.get_image(), x) < 1e-5
-    os.environ["PDWT_FORCE_GENERIC"] = "1"
-    try:
-        G = Wavelets(x, "db7", 3)
-        G.forward()
-        for i in range(G.ncoeffs):
-            assert bitexact(G.get_coeff(i), coeffs[i]), i
-        G.inverse()
-        assert bitexact(G.get_image(), W.get_image())
-    finally:
-        del os.environ["PDWT_FORCE_GENERIC"]
+    for other in ("fused", "generic"):
+        os.environ["PDWT_PATH"] = other
+        try:
+            G = Wavelets(x, "db7", 3)
+            G.forward()
+            for i in range(G.ncoeffs):
+                assert bitexact(G.get_coeff(i), coeffs[i]), (other, i)
+            G.inverse()
+            assert bitexact(G.get_image(), W.get_image()), other
+        finally:
+            del os.environ["PDWT_PATH"]
     # linearity: W(2x) == 2 W(x) exactly (power-of-two scaling commutes with every rounding)
     W2 = Wavelets(2 * x, "db7", 3)
     W2.forward()
