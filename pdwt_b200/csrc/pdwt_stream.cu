@@ -26,7 +26,9 @@
 //
 // Shapes these kernels take: even hlen in [4, 20], even Nr, Nc % 4 == 0, Nc large enough that a strip wraps at
 // most once, 16-byte aligned planes.  Everything else goes to pdwt_fused.cu / pdwt_generic.cu.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "pdwt_common.cuh"
 
@@ -107,6 +109,32 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 
 constexpr int round4(int n) { return (n + 3) & ~3; }
 
+// Programmatic dependent launch: the level kernels of one transform are queued back to back on one stream; each lets
+// its successor's CTAs start (launch latency, barrier init, address set-up) while it is still draining, and blocks
+// at pdl_wait() until its predecessor has completed and flushed before touching global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename Kern, typename Params>
+static cudaError_t launch_pdl(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t s, const Params& p)
+{
+    // measured on B200 (C2): overlapping the next level's launch this way costs ~6% (its CTAs hold shared memory and
+    // registers while they spin), so it is off unless PDWT_PDL=1
+    static const bool no_pdl = getenv("PDWT_PDL") == nullptr;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 // One lane of the (converged) warp, chosen by the hardware; ptxas keeps the guarded block uniform, so the bulk copies
 // inside compile to a single UBLKCP each instead of a per-lane loop.
 __device__ __forceinline__ bool elect_one()
@@ -123,26 +151,40 @@ __device__ __forceinline__ bool elect_one()
 }
 
 // ================================================================================================== forward
-// CTA = ONE warp: every quantity derived from blockIdx is provably warp-uniform, which is what lets ptxas keep the
-// filter taps in uniform registers (FFMA2 R, R, UR, R) and the loop control on the uniform datapath.
-template <int HLEN, int NS_ = 8>
+// Warp-specialised CTA: NCW consumer warps + ONE producer warp.
+//   * producer: feeds every consumer's private ring through the TMA engine.  Issuing a TMA request stalls the issuing
+//     warp for 100+ cycles (measured with clock64: two cp.async.bulk per row pair cost a consumer ~300 of its ~770
+//     cycles), so no arithmetic warp ever issues one.  Interior super-slots take ONE tensor-map request
+//     (cp.async.bulk.tensor.3d, box WW x SR x 1); super-slots that need the periodic extension of
+//     separable.cu:114-121 (image edges) are staged row by row with cp.async.bulk pieces, wrapped columns included.
+//   * consumer: owns a strip of 64 output columns, waits on its ring's "full" mbarrier, runs the FFMA2 row pass and
+//     scatter column pass out of registers, and hands super-slots back through an "empty" mbarrier.
+// Every loop bound derives from blockIdx (all consumers of a CTA share the row chunk) and the warp index is read through
+// a shuffle, so ptxas can prove the control flow warp-uniform and keeps the filter taps in uniform registers
+// (FFMA2 R, R, UR, R) and the loop control on the uniform datapath.
+template <int HLEN>
 struct FwdGeom {
     static constexpr int NC = 2;                        // output columns per lane
     static constexpr int H2 = HLEN / 2;
     static constexpr int C = H2 - 1;                    // analysis centre (even hlen), separable.cu:103-107
     static constexpr int AL = round4(C);                // the strip starts AL input columns left of 2*k0 (16-byte aligned)
     static constexpr int SH = AL - C;                   // first useful column inside the staged strip
-    static constexpr int WO = 32 * NC;                  // output columns per warp
+    static constexpr int WO = 32 * NC;                  // output columns per consumer warp
     static constexpr int WW = round4(SH + 2 * WO + HLEN - 2);  // staged input columns per row
     static constexpr int NV = (SH + 2 * NC - 2 + HLEN + 3) / 4;  // 16-byte vectors a lane reads per row
-    static constexpr int NS = NS_;                      // ring slots (2 input rows each)
-    static constexpr int SLOT = 2 * WW;                 // floats per slot
-    static constexpr size_t SMEM = (size_t)NS * (SLOT * sizeof(float) + sizeof(u64));
+    static constexpr int NCW = 4;                       // consumer warps per CTA
+    static constexpr int SR = 8;                        // input rows per super-slot (one TMA request)
+    static constexpr int NSS = 3;                       // super-slots per consumer ring
+    static constexpr int SSB = SR * WW * 4;             // bytes per super-slot (multiple of 128)
+    static constexpr int THREADS = (NCW + 1) * 32;
+    static constexpr size_t SMEM = (size_t)NCW * NSS * SSB + NCW * NSS * 2 * sizeof(u64) + 128;
     static_assert(4 * (NV - 1) + 2 * NC * 31 + 4 <= WW, "lane window exceeds the staged strip");
+    static_assert(SSB % 128 == 0 && WW <= 256 && SR % 2 == 0, "tensor-map box constraints");
 };
 
 template <int HLEN>
 struct FwdParams {
+    CUtensorMap tm;   // (Nc, Nr, batch) fp32 tensor over the source planes, box (WW, SR, 1); valid iff use_tm
     float2 lh[HLEN];  // (L[hlen-1-j], H[hlen-1-j]): row-pass tap pairs in the reference's accumulation order
     float ly[HLEN];   // L[hlen-1-j]
     float hy[HLEN];   // H[hlen-1-j]
@@ -151,80 +193,104 @@ struct FwdParams {
     size_t s_src, s_a, s_d;  // plane strides (floats)
     int Nr, Nc, nr, nc;      // input and output plane sizes
     int TH;                  // output rows per chunk
-    int ncb, nrc;            // column blocks, row chunks; grid = ncb * nrc * batch work items
+    int ncg, nrc;            // column groups (NCW strips each), row chunks; grid = ncg * nrc * batch CTAs
+    int use_tm;
 };
 
-// DBG != 0 builds timing experiments only (wrong results): 1 = no arithmetic, 2 = no staging / no barrier waits
-template <int HLEN, int NS_ = 8, int DBG = 0>
-__global__ void __launch_bounds__(32, 12) k_fwd2d_stream(const __grid_constant__ FwdParams<HLEN> p)
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm, int x, int y, int z, unsigned bar)
 {
-    using G = FwdGeom<HLEN, NS_>;
-    constexpr int H2 = G::H2, NC = G::NC, NS = G::NS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int HLEN>
+__global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) k_fwd2d_stream(const __grid_constant__ FwdParams<HLEN> p)
+{
+    using G = FwdGeom<HLEN>;
+    constexpr int H2 = G::H2, NC = G::NC, NSS = G::NSS, SR = G::SR, NCW = G::NCW;
+    extern __shared__ unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
     const int item = blockIdx.x;
 
-    float* ring = reinterpret_cast<float*>(smem_raw);
-    const unsigned ring_s = smem_u32(ring);
-    const unsigned bar_s = ring_s + NS * G::SLOT * 4;
+    const unsigned ring_s = (smem_u32(smem_raw) + 127u) & ~127u;   // tensor-map destinations are 128-byte aligned
+    const unsigned bar_s = ring_s + NCW * NSS * G::SSB;            // full[w][s] at +16*(w*NSS+s), empty right behind it
 
-    const int cb = item % p.ncb, rest = item / p.ncb, rc = rest % p.nrc, plane = rest / p.nrc;
-    const int k0 = cb * G::WO, y0 = rc * p.TH;
+    const int cg = item % p.ncg, rest = item / p.ncg, rc = rest % p.nrc, plane = rest / p.nrc;
+    const int y0 = rc * p.TH;
     const int ny = min(p.TH, p.nr - y0);
     const int npairs = ny + H2 - 1;          // input row pairs this chunk consumes
-    const int xs = 2 * k0 - G::AL;           // first staged input column (multiple of 4, may be < 0)
-    const float* src = p.src + (size_t)plane * p.s_src;
+    const int nss = (2 * npairs + SR - 1) / SR;   // super-slots per consumer
+    const int vr0 = 2 * y0 - G::C;           // first input row (virtual: < 0 or >= Nr wraps around)
+    const int nstrips = min(NCW, (p.nc - cg * NCW * G::WO + G::WO - 1) / G::WO);   // strips of this CTA inside the image
 
-    // column pieces of one staged row: main part, and the part that wraps around the image (periodic extension,
-    // separable.cu:114-121, even sizes); byte counts and offsets are the same for every row
-    const int x_lo = max(xs, 0), x_hi = min(xs + G::WW, p.Nc);
-    const unsigned main_dst = (x_lo - xs) * 4, main_bytes = (x_hi - x_lo) * 4;
-    const int wrap_src = (xs < 0) ? p.Nc + xs : 0;
-    const unsigned wrap_dst = (xs < 0) ? 0 : (p.Nc - xs) * 4;
-    const unsigned wrap_bytes = (xs < 0) ? -xs * 4 : ((xs + G::WW > p.Nc) ? (xs + G::WW - p.Nc) * 4 : 0);
-
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < NS; s++) mbar_init(bar_s + 8 * s, 1);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NCW * NSS * 2; i++) mbar_init(bar_s + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
+    __syncthreads();   // the only block-wide barrier: after it the warps only meet through mbarriers
+    pdl_launch_dependents();
+    pdl_wait();        // the previous level's kernel (or whatever wrote `src`) has completed
 
-    // ---- staging state (all warp-uniform).  Row pieces go through the TMA engine one cp.async.bulk each; source
-    // pointer, ring position and barrier advance incrementally so a refill costs a handful of uniform instructions.
-    int frow = 2 * y0 - G::C;                // next input row to stage; virtual index wrapped once here ...
-    frow += (frow < 0) ? p.Nr : 0;
-    const char* gnext = reinterpret_cast<const char*>(src + (size_t)frow * p.Nc + x_lo);
-    int to_wrap = p.Nr - frow;               // ... and every time this many more rows have been staged
-    const size_t row_bytes = (size_t)p.Nc * 4, plane_bytes = row_bytes * p.Nr;
-    const long long wrap_delta = ((long long)wrap_src - x_lo) * 4;
-    // stage input row pair q into the ring slot at byte offset `soff` (its barrier: `bar`)
-    auto fill = [&](int q, unsigned soff, unsigned bar) {
-        if (DBG == 2) return;
-        if (q < npairs) {
-            if (elect_one()) {
-                mbar_expect_tx(bar, 2 * G::WW * 4);
-                const char* g0 = gnext;
-                const char* g1 = (to_wrap == 1) ? gnext + row_bytes - plane_bytes : gnext + row_bytes;
-                const unsigned dst = ring_s + soff;
-                bulk_g2s(dst + main_dst, g0, main_bytes, bar);
-                bulk_g2s(dst + G::WW * 4 + main_dst, g1, main_bytes, bar);
-                if (wrap_bytes) {
-                    bulk_g2s(dst + wrap_dst, g0 + wrap_delta, wrap_bytes, bar);
-                    bulk_g2s(dst + G::WW * 4 + wrap_dst, g1 + wrap_delta, wrap_bytes, bar);
+    if (warp == NCW) {
+        // ===================================================================================== producer warp
+        const float* src = p.src + (size_t)plane * p.s_src;
+        for (int k = 0; k < nss; k++) {
+            const int slot = k % NSS;
+            const unsigned par_e = ((k / NSS) + 1) & 1;   // parity of the consumer's (k/NSS)-th release of this slot
+            int row0 = vr0 + SR * k;
+            // rows needed from this super-slot all inside the image? (rows past the chunk's last pair may fall outside:
+            // the tensor request zero-fills them and nobody reads them)
+            const int last_needed = min(row0 + SR, vr0 + 2 * npairs) - 1;
+            const bool rows_in = row0 >= 0 && last_needed < p.Nr;
+            row0 += (row0 < 0) ? p.Nr : 0;
+            row0 -= (row0 >= p.Nr) ? p.Nr : 0;
+            for (int w = 0; w < nstrips; w++) {
+                const unsigned full = bar_s + 16 * (w * NSS + slot), empty = full + 8;
+                if (k >= NSS) mbar_wait(empty, par_e);
+                if (elect_one()) {
+                    const int xs = 2 * (cg * NCW + w) * G::WO - G::AL;
+                    const unsigned dst = ring_s + (w * NSS + slot) * G::SSB;
+                    mbar_expect_tx(full, G::SSB);
+                    if (p.use_tm && rows_in && xs >= 0 && xs + G::WW <= p.Nc) {
+                        tma_load_3d(dst, &p.tm, xs, vr0 + SR * k, plane, full);
+                    } else {
+                        // periodic extension (separable.cu:114-121, even sizes): wrapped row index, and a second
+                        // copy for the columns that wrap around the image
+                        const int x_lo = max(xs, 0), x_hi = min(xs + G::WW, p.Nc);
+                        const unsigned main_dst = (x_lo - xs) * 4, main_bytes = (x_hi - x_lo) * 4;
+                        const int wrap_src = (xs < 0) ? p.Nc + xs : 0;
+                        const unsigned wrap_dst = (xs < 0) ? 0 : (p.Nc - xs) * 4;
+                        const unsigned wrap_bytes =
+                            (xs < 0) ? -xs * 4 : ((xs + G::WW > p.Nc) ? (xs + G::WW - p.Nc) * 4 : 0);
+                        int row = row0;
+#pragma unroll 1
+                        for (int r = 0; r < SR; r++) {
+                            const float* g = src + (size_t)row * p.Nc;
+                            bulk_g2s(dst + r * G::WW * 4 + main_dst, g + x_lo, main_bytes, full);
+                            if (wrap_bytes) bulk_g2s(dst + r * G::WW * 4 + wrap_dst, g + wrap_src, wrap_bytes, full);
+                            row = (row + 1 == p.Nr) ? 0 : row + 1;
+                        }
+                    }
                 }
-            }
-            gnext += 2 * row_bytes;
-            to_wrap -= 2;
-            if (to_wrap <= 0) {
-                gnext -= plane_bytes;
-                to_wrap += p.Nr;
+                __syncwarp();
             }
         }
-    };
-#pragma unroll 1
-    for (int q = 0; q < NS; q++) fill(q, q * G::SLOT * 4, bar_s + 8 * q);
+        return;
+    }
+
+    // ========================================================================================= consumer warps
+    if (warp >= nstrips) return;
+    const int k0 = (cg * NCW + warp) * G::WO;
+    const unsigned my_ring = ring_s + warp * NSS * G::SSB;
+    const unsigned my_bar = bar_s + 16 * warp * NSS;
 
     // pending output rows: slot (y mod H2); pairs (A,V) and (H,D) per owned column
     u64 aLV[H2][NC], aHD[H2][NC];
@@ -240,14 +306,11 @@ __global__ void __launch_bounds__(32, 12) k_fwd2d_stream(const __grid_constant__
     float* oH = p.Hb + (size_t)plane * p.s_d + o0;
     float* oV = p.V + (size_t)plane * p.s_d + o0;
     float* oD = p.D + (size_t)plane * p.s_d + o0;
-    const float* lane_ring = ring + 2 * NC * lane;
+    // this lane's window inside a staged row, as a generic pointer (plain loads keep their order w.r.t. the barriers)
+    const char* lane_ring = static_cast<const char*>(__cvta_shared_to_generic(my_ring)) + 2 * NC * lane * 4;
 
     // one input row: row pass on the lane's window, then the column pass scatters the fresh (lo, hi) pair
     auto row_step = [&](const float (&xv)[G::NV * 4], const int sb, const int r) {
-        if (DBG == 1) {
-            aLV[sb][0] = pack2(xv[0] + xv[G::NV * 4 - 1], xv[5]);
-            return;
-        }
         // row pass, w_kern_forward_pass1 (separable.cu:91-131): (lo, hi)[c] = sum_j x[2k - C + j] * (L, H)[hlen-1-j]
         u64 lohi[NC];
 #pragma unroll
@@ -274,41 +337,44 @@ __global__ void __launch_bounds__(32, 12) k_fwd2d_stream(const __grid_constant__
             }
         }
     };
-    auto load_row = [&](float (&xv)[G::NV * 4], const float* rowp) {
+    auto load_row = [&](float (&xv)[G::NV * 4], const char* rowp) {
+        const float4* rp = reinterpret_cast<const float4*>(rowp);
 #pragma unroll
         for (int i = 0; i < G::NV; i++) {
-            const float4 f = *reinterpret_cast<const float4*>(rowp + 4 * i);
+            const float4 f = rp[i];
             xv[4 * i] = f.x; xv[4 * i + 1] = f.y; xv[4 * i + 2] = f.z; xv[4 * i + 3] = f.w;
         }
     };
 
-    // Software pipeline over row pairs: while pair q is being computed its successor's barrier is probed (the probe's
-    // latency hides behind the FFMA2s); at the end of the pair the first row of pair q+1 is already pulled into
-    // registers, so a lone warp keeps its FP32 pipe busy without help from other warps.
-    int q = 0;
-    unsigned soff = 0, bar = bar_s, parity = 0;   // ring position of row pair q
+    // Software pipeline over row pairs: the first row of pair q+1 is pulled into registers at the end of pair q, and
+    // the "full" barrier of the next super-slot is probed while the last pair of the current one is computed.
+    int q = 0, pin = 0;                           // pair index, pair within its super-slot
+    unsigned soff = 0, bar = my_bar, parity = 0;  // ring position (byte offset, full barrier, phase) of the super-slot
     float xa[G::NV * 4], xb[G::NV * 4];
-    if (DBG != 2) mbar_wait(bar, parity);
+    mbar_wait(bar, parity);
     load_row(xa, lane_ring);
     for (;;) {
 #pragma unroll
         for (int sb = 0; sb < H2; sb++) {  // body: H2 row pairs = hlen input rows; all register indices static
-            const float* rowp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(lane_ring) + soff);
-            load_row(xb, rowp + G::WW);
-            // ring position of pair q+1
-            unsigned nsoff = soff + G::SLOT * 4, nbar = bar + 8, nparity = parity;
-            if (nsoff == NS * G::SLOT * 4) {
+            const char* rowa = lane_ring + soff + pin * (2 * G::WW * 4);
+            load_row(xb, rowa + G::WW * 4);
+            const bool more = q + 1 < npairs;
+            const bool last_in_ss = pin == SR / 2 - 1;
+            unsigned nsoff = soff + G::SSB, nbar = bar + 16, nparity = parity;
+            if (nsoff == NSS * G::SSB) {
                 nsoff = 0;
-                nbar = bar_s;
+                nbar = my_bar;
                 nparity ^= 1;
             }
-            const bool more = q + 1 < npairs;
-            const unsigned ready = (more && DBG != 2) ? mbar_test(nbar, nparity) : 1u;
+            unsigned ready = 1;
+            if (last_in_ss && more) ready = mbar_test(nbar, nparity);
             row_step(xa, sb, 0);
             row_step(xb, sb, 1);
-            // every lane has consumed both rows of this slot: hand it back to the TMA engine
-            __syncwarp();
-            fill(q + NS, soff, bar);
+            if (last_in_ss) {
+                // every lane has consumed all rows of this super-slot: hand it back to the producer
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + 8);
+            }
             // the output row that received its last tap (j = hlen-1) in this pair
             if (q >= H2 - 1) {
                 const int sl = (sb + 1) % H2;
@@ -326,14 +392,38 @@ __global__ void __launch_bounds__(32, 12) k_fwd2d_stream(const __grid_constant__
                 oA += p.nc; oH += p.nc; oV += p.nc; oD += p.nc;
             }
             if (!more) return;
-            if (!ready) mbar_wait(nbar, nparity);
             q++;
-            soff = nsoff;
-            bar = nbar;
-            parity = nparity;
-            load_row(xa, reinterpret_cast<const float*>(reinterpret_cast<const char*>(lane_ring) + soff));
+            if (last_in_ss) {
+                if (!ready) mbar_wait(nbar, nparity);
+                soff = nsoff;
+                bar = nbar;
+                parity = nparity;
+                pin = 0;
+            } else {
+                pin++;
+            }
+            load_row(xa, lane_ring + soff + pin * (2 * G::WW * 4));
         }
     }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
 }
 
 template <int HLEN>
@@ -342,7 +432,7 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
 {
     using G = FwdGeom<HLEN>;
     const int nr = Nr / 2, nc = Nc / 2;
-    // shapes the bulk-copy staging can serve (see the file header); 0 = "not handled"
+    // shapes the TMA staging can serve (see the file header); 0 = "not handled"
     if ((Nr & 1) || (Nc & 3) || Nc < G::WW || Nr < HLEN) return 0;
     if ((((uintptr_t)src.p) & 15) || (src.stride & 3)) return 0;
     if ((((uintptr_t)A.p | (uintptr_t)H.p | (uintptr_t)V.p | (uintptr_t)D.p) & 7) || (A.stride & 1) || (H.stride & 1))
@@ -353,6 +443,18 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
         configured = true;
     }
     FwdParams<HLEN> p;
+    memset(&p.tm, 0, sizeof p.tm);
+    p.use_tm = 0;
+    if (EncodeTiledFn enc = encode_tiled_fn()) {
+        const cuuint64_t dims[3] = {(cuuint64_t)Nc, (cuuint64_t)Nr, (cuuint64_t)batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)Nc * 4, (cuuint64_t)src.stride * 4};  // bytes, dims 1 and 2
+        const cuuint32_t box[3] = {(cuuint32_t)G::WW, (cuuint32_t)G::SR, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(&p.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)src.p, dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            p.use_tm = (getenv("PDWT_NO_TENSORMAP") == nullptr);
+    }
     for (int j = 0; j < HLEN; j++) {
         p.lh[j] = make_float2(t.L[HLEN - 1 - j], t.H[HLEN - 1 - j]);
         p.ly[j] = t.L[HLEN - 1 - j];
@@ -361,33 +463,18 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
     p.src = src.p; p.A = A.p; p.Hb = H.p; p.V = V.p; p.D = D.p;
     p.s_src = src.stride; p.s_a = A.stride; p.s_d = H.stride;
     p.Nr = Nr; p.Nc = Nc; p.nr = nr; p.nc = nc;
-    p.ncb = idiv_up(nc, G::WO);
-    // chunk height: aim at >= 4 worker warps per SM sub-partition's worth of items (148 SMs x 16 resident warps),
-    // but never below 16 output rows (the vertical halo is hlen-2 input rows per chunk)
-    // chunk height: the largest power of two in [8, 64] that still yields ~1.5 worker warps per SM sub-partition
+    p.ncg = idiv_up(nc, G::WO * G::NCW);
+    // chunk height: the largest power of two in [8, 64] that still yields ~1.5 consumer warps per SM sub-partition
     // (148 x 4 of them); the vertical halo costs hlen-2 input rows of row-pass work per chunk
     int TH = 64;
-    while (TH > 8 && (long long)p.ncb * idiv_up(nr, TH) * batch < 900) TH >>= 1;
+    while (TH > 8 && (long long)idiv_up(nc, G::WO) * idiv_up(nr, TH) * batch < 900) TH >>= 1;
     if (const char* e = getenv("PDWT_TH")) TH = atoi(e) > 0 ? atoi(e) : TH;
     p.TH = TH;
     p.nrc = idiv_up(nr, TH);
-    const long long nitems = (long long)p.ncb * p.nrc * batch;
-    if (nitems > 0x7fffffff) return 0;
+    const long long nctas = (long long)p.ncg * p.nrc * batch;
+    if (nctas > 0x7fffffff) return 0;
     PDWT_PROF(prof_tag("k_fwd2d_stream", Nr, Nc), s);
-#ifdef PDWT_EXPERIMENTS
-    if (HLEN == 14) {
-        const char* e = getenv("PDWT_DBG");
-        const int dbg = e ? atoi(e) : 0;
-        if (dbg == 1) { k_fwd2d_stream<HLEN, 8, 1><<<(unsigned)nitems, 32, G::SMEM, s>>>(p); PDWT_LAUNCH_CHECK(); return 1; }
-        if (dbg == 2) { k_fwd2d_stream<HLEN, 8, 2><<<(unsigned)nitems, 32, G::SMEM, s>>>(p); PDWT_LAUNCH_CHECK(); return 1; }
-        if (dbg == 16) {
-            using G16 = FwdGeom<HLEN, 16>;
-            cudaFuncSetAttribute(k_fwd2d_stream<HLEN, 16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G16::SMEM);
-            k_fwd2d_stream<HLEN, 16, 0><<<(unsigned)nitems, 32, G16::SMEM, s>>>(p); PDWT_LAUNCH_CHECK(); return 1;
-        }
-    }
-#endif
-    k_fwd2d_stream<HLEN><<<(unsigned)nitems, 32, G::SMEM, s>>>(p);
+    PDWT_CUDA(launch_pdl(k_fwd2d_stream<HLEN>, (unsigned)nctas, G::THREADS, G::SMEM, s, p));
     PDWT_LAUNCH_CHECK();
     return 1;
 }
@@ -397,13 +484,14 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
 // (2m, 2m+1):   even output: coefficients m-CC+j,        taps  IL/IH[hlen-1-(2j+1-SHIFT)]
 //               odd  output: coefficients m-CC+SHIFT+j,  taps  IL/IH[hlen-1-(2j+SHIFT)]        j = 0 .. hlen/2-1
 // with CC = (hlen/2)/2 and SHIFT = 1 when hlen/2 is even (the reference's "virtual id for shift").
-template <int HLEN>
+template <int HLEN, int PF_ = 2>
 struct InvGeom {
     static constexpr int H2 = HLEN / 2;
     static constexpr int CC = H2 / 2;
     static constexpr int SHIFT = (H2 & 1) ? 0 : 1;
     static constexpr int WIN = H2 + SHIFT;              // coefficient rows (columns) behind one output pair
-    static constexpr int NSLOT = WIN + 1;               // register window: WIN rows + one row of prefetch
+    static constexpr int PF = PF_;                      // coefficient rows loaded ahead of use (global-load latency)
+    static constexpr int NSLOT = WIN + PF;              // register window: WIN rows + the rows in flight
     static constexpr int ALC = (CC + 1) & ~1;           // the strip starts ALC coefficient columns left of k0 (even)
     static constexpr int SHC = ALC - CC;
     static constexpr int NP = (SHC + WIN + 3 + 1) & ~1; // (t1,t2) pairs a row-synthesis lane reads (4 coefficient columns)
@@ -429,10 +517,10 @@ struct InvParams {
 // chunk lane) and the readers (lane -> chunks 2*lane' + v) are bank-conflict free
 __device__ __forceinline__ int swz(int q) { return q ^ ((q >> 3) & 1); }
 
-template <int HLEN>
+template <int HLEN, int PF_ = 2>
 __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__ InvParams<HLEN> p)
 {
-    using G = InvGeom<HLEN>;
+    using G = InvGeom<HLEN, PF_>;
     constexpr int H2 = G::H2, NSLOT = G::NSLOT, WIN = G::WIN, SHIFT = G::SHIFT;
     __shared__ __align__(16) float tile[2][2][64 * 2];   // [buffer][output row parity][(t1,t2) x 64]
     const int lane = threadIdx.x;
@@ -472,8 +560,11 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
     };
 #pragma unroll
     for (int i = 0; i < NSLOT; i++) wA[i] = wH[i] = wV[i] = wD[i] = 0ull;
+    pdl_launch_dependents();
+    pdl_wait();        // the previous level's kernel (or whatever wrote the coefficients) has completed
 #pragma unroll
-    for (int i = 0; i < WIN; i++) load_row(i);
+    for (int i = 0; i < WIN + G::PF - 1; i++)
+        if (i < nm + WIN - 1) load_row(i);
 
     // ---- row synthesis side: lanes 0..LPR-1 take the even output row, lanes 16..16+LPR-1 the odd one; each turns 4
     // coefficient columns into 8 pixels
@@ -493,7 +584,7 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
 #pragma unroll
         for (int sb = 0; sb < NSLOT; sb++) {  // body: NSLOT output row pairs; all register indices static
             if (s >= nm) return;
-            if (s + 1 < nm) load_row((sb + WIN) % NSLOT);   // prefetch the row the next pair adds
+            if (s + G::PF < nm) load_row((sb + NSLOT - 1) % NSLOT);   // the row that pair s + PF adds to the window
             // column synthesis, w_kern_inverse_pass1 (separable.cu:246-289): t1 = IL_y(A) + IH_y(H), t2 = IL_y(V) + IH_y(D)
 #pragma unroll
             for (int par = 0; par < 2; par++) {
@@ -575,7 +666,7 @@ static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2
     const long long nitems = (long long)p.ncb * p.nrc * batch;
     if (nitems > 0x7fffffff) return 0;
     PDWT_PROF(prof_tag("k_inv2d_stream", Mr, Mc), s);
-    k_inv2d_stream<HLEN><<<(unsigned)nitems, 32, 0, s>>>(p);
+    PDWT_CUDA(launch_pdl(k_inv2d_stream<HLEN>, (unsigned)nitems, 32, 0, s, p));
     PDWT_LAUNCH_CHECK();
     return 1;
 }
