@@ -38,9 +38,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (Nr, Nc, wavelet, levels)
-    "c2": (4096, 4096, "db7", 3),       # BASELINE.json configs[1] -- the configuration the metric is quoted on
-    "c5img": (2048, 2048, "db7", 3),    # one image of configs[4]
+    # name: (Nr, Nc, wavelet, levels, images per GPU and step)
+    "c2": (4096, 4096, "db7", 3, 1),     # BASELINE.json configs[1] -- the configuration the metric is quoted on
+    "c5img": (2048, 2048, "db7", 3, 1),  # one image of configs[4]
+    "c5": (2048, 2048, "db7", 3, 64),    # configs[4]: 512 images of 2048^2 over 8 GPUs = 64 per GPU, one batched object
 }
 ROTATE = 4
 METRIC = "Mpixels/s fwd+inv 2D DWT db7 L3 4096^2"
@@ -156,27 +157,30 @@ def run_ours(args):
     from pdwt_b200 import Wavelets
 
     world, rank, local = dist_setup(args.gpus)
-    Nr, Nc, wname, levels = WORKLOADS[args.workload]
-    npx = Nr * Nc
+    Nr, Nc, wname, levels, nimg = WORKLOADS[args.workload]
+    npx = Nr * Nc * nimg
+    rotate = ROTATE if nimg == 1 else 1      # a 64-image batch (1 GiB) is 8x the L2 by itself
     L = pdwt_b200.lib()
     if L.pdwt_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device -- pdwt_b200 has no CPU fallback")
 
-    imgs = [seeded_image((Nr, Nc), 1000 * rank + i) for i in range(ROTATE)]
+    shape = (Nr, Nc) if nimg == 1 else (nimg, Nr, Nc)
+    imgs = [seeded_image(shape, 1000 * rank + i) for i in range(rotate)]
     Ws = [Wavelets(torch.from_numpy(im).cuda(), wname, levels) for im in imgs]
     stream = torch.cuda.current_stream()
+    ROT = rotate
 
     def step(i):
-        W = Ws[i % ROTATE]
+        W = Ws[i % ROT]
         W.forward()
         W.inverse()
 
     for i in range(args.warmup):
         step(i)
     # parity spot check before anything is timed: perfect reconstruction of the rotating images
-    rec = Ws[(args.warmup - 1) % ROTATE].get_image() if args.warmup else None
+    rec = Ws[(args.warmup - 1) % ROT].get_image() if args.warmup else None
     if rec is not None:
-        ref = imgs[(args.warmup - 1) % ROTATE]
+        ref = imgs[(args.warmup - 1) % ROT]
         err = float(np.abs(rec - ref).max() / np.abs(ref).max())
         if not err < 1e-5:
             raise SystemExit(f"bench.py: fwd+inv does not reconstruct the image (err {err:.3e})")
@@ -195,12 +199,12 @@ def run_ours(args):
 
         # ---- end to end through the public API with pinned host buffers
         h_in = [torch.from_numpy(im).pin_memory() for im in imgs]
-        h_out = torch.empty((Nr, Nc), dtype=torch.float32).pin_memory()
+        h_out = torch.empty(shape, dtype=torch.float32).pin_memory()
         out_np = h_out.numpy()
 
         def e2e_step(i):
-            W = Ws[i % ROTATE]
-            W.set_image(h_in[i % ROTATE].numpy())      # H2D (pinned), wt.cu:427
+            W = Ws[i % ROT]
+            W.set_image(h_in[i % ROT].numpy())         # H2D (pinned), wt.cu:427
             W.forward()
             W.inverse()
             W.get_image(out_np)                        # D2H (pinned), wt.cu:421
@@ -235,6 +239,7 @@ def run_ours(args):
         top = max(kernels, key=lambda k: kernels[k]["total_ms"])
         ab = algorithmic_bytes(top)
         if ab:
+            ab *= nimg
             ach = ab / (kernels[top]["avg_us"] * 1e-6) / 1e9
             roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": None, "algorithmic_bytes_per_launch": ab,
@@ -253,9 +258,11 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 5), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {Nr}x{Nc} float32, {wname}, {levels} levels, separable DWT, "
-                               f"forward()+inverse() of one image per step (BASELINE.json configs[1])",
-                   "l2": f"steps rotate over {ROTATE} Wavelets objects with distinct images/buffers (~1 GiB touched "
-                         f"between reuses, > 126 MB L2); no explicit flush",
+                               f"forward()+inverse() of {nimg} image(s) per GPU and step "
+                               f"(BASELINE.json configs[{1 if args.workload == 'c2' else 4}])",
+                   "l2": (f"steps rotate over {ROTATE} Wavelets objects with distinct images/buffers (~1 GiB touched "
+                          f"between reuses, > 126 MB L2); no explicit flush") if nimg == 1 else
+                         f"one batched object of {nimg} images (inputs {4 * npx >> 20} MiB > 126 MB L2)",
                    "per_gpu": "every rank runs this workload on its own images; no data-path collective"},
         "e2e": {"value": round(e2e_val, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": 4 * npx,
                 "d2h_bytes_per_step": 4 * npx, "ms_per_step": round(ms_e2e / args.steps, 4),
@@ -270,6 +277,8 @@ def run_ours(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_port_baseline(Nr, Nc, wname, levels, iters=3)
+    if args.workload != "c2":
+        out["metric"] = f"Mpixels/s fwd+inv 2D DWT db7 L3 {Nr}^2 x {nimg} per GPU"
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -299,7 +308,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    Nr, Nc, wname, levels = WORKLOADS[args.workload]
+    Nr, Nc, wname, levels, nimg = WORKLOADS[args.workload]
+    if nimg != 1:
+        raise SystemExit("--impl reference: the reference has no batch dimension; use c2 or c5img")
     npx = Nr * Nc
     cfg = {"workload": f"{args.workload}: {Nr}x{Nc} float32, {wname}, {levels} levels, separable DWT, "
                        f"forward()+inverse() of one image per step (BASELINE.json configs[1])"}
