@@ -115,6 +115,7 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = os.environ.get("PDWT_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -246,7 +247,7 @@ def run_ours(args):
                     "avg_us": round(kernels[top]["avg_us"], 2), "peak_source": peak_src,
                     "kernel_share_of_step": round(kernels[top]["total_ms"] / sum(v["total_ms"] for v in kernels.values()), 3)}
             tr = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the ncu capture
-            if os.path.exists(tr):
+            if os.path.exists(tr) and args.workload == "c2":
                 roof["traffic"] = json.load(open(tr)).get(top.split("[")[0])
 
     value = world * npx * args.steps / (ms_dev * 1e-3) / 1e6

@@ -484,20 +484,23 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
 // (2m, 2m+1):   even output: coefficients m-CC+j,        taps  IL/IH[hlen-1-(2j+1-SHIFT)]
 //               odd  output: coefficients m-CC+SHIFT+j,  taps  IL/IH[hlen-1-(2j+SHIFT)]        j = 0 .. hlen/2-1
 // with CC = (hlen/2)/2 and SHIFT = 1 when hlen/2 is even (the reference's "virtual id for shift").
-template <int HLEN, int PF_ = 2>
+template <int HLEN>
 struct InvGeom {
     static constexpr int H2 = HLEN / 2;
     static constexpr int CC = H2 / 2;
     static constexpr int SHIFT = (H2 & 1) ? 0 : 1;
     static constexpr int WIN = H2 + SHIFT;              // coefficient rows (columns) behind one output pair
-    static constexpr int PF = PF_;                      // coefficient rows loaded ahead of use (global-load latency)
-    static constexpr int NSLOT = WIN + PF;              // register window: WIN rows + the rows in flight
+    static constexpr int NSLOT = WIN + 1;               // register window: WIN rows + the row being pulled from the ring
+    static constexpr int DEPTH = 7;                     // coefficient rows in flight global -> shared (cp.async groups)
+    static constexpr int RS = DEPTH + 1;                // ring slots (one more than in flight: never refill the slot just read)
+    static constexpr int ROWB = 4 * 64 * 4;             // ring bytes per coefficient row: A,H,V,D x 64 columns
     static constexpr int ALC = (CC + 1) & ~1;           // the strip starts ALC coefficient columns left of k0 (even)
     static constexpr int SHC = ALC - CC;
     static constexpr int NP = (SHC + WIN + 3 + 1) & ~1; // (t1,t2) pairs a row-synthesis lane reads (4 coefficient columns)
     static constexpr int WOUT = 4 * ((64 - NP) / 4) + 4; // coefficient columns a warp turns into pixels
     static constexpr int LPR = WOUT / 4;                // row-synthesis lanes per output row (<= 16)
-    static constexpr size_t SMEM = 2 * 2 * 64 * 8;      // double-buffered tile: 2 output rows x 64 (t1,t2) pairs
+    static constexpr size_t TILEB = 2 * 2 * 64 * 8;     // double-buffered tile: 2 output rows x 64 (t1,t2) pairs
+    static constexpr size_t SMEM = TILEB + (size_t)RS * ROWB;
     static_assert(LPR <= 16 && WOUT - 4 + NP <= 64, "row-synthesis window exceeds the strip");
 };
 
@@ -517,12 +520,25 @@ struct InvParams {
 // chunk lane) and the readers (lane -> chunks 2*lane' + v) are bank-conflict free
 __device__ __forceinline__ int swz(int q) { return q ^ ((q >> 3) & 1); }
 
-template <int HLEN, int PF_ = 2>
+// 8-byte asynchronous copy global -> shared (LDGSTS), tracked by cp.async groups
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int HLEN>
 __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__ InvParams<HLEN> p)
 {
-    using G = InvGeom<HLEN, PF_>;
+    using G = InvGeom<HLEN>;
     constexpr int H2 = G::H2, NSLOT = G::NSLOT, WIN = G::WIN, SHIFT = G::SHIFT;
-    __shared__ __align__(16) float tile[2][2][64 * 2];   // [buffer][output row parity][(t1,t2) x 64]
+    extern __shared__ __align__(16) unsigned char smem_inv[];
+    float (*tile)[2][64 * 2] = reinterpret_cast<float (*)[2][64 * 2]>(smem_inv);   // [buffer][output row parity][(t1,t2) x 64]
     const int lane = threadIdx.x;
     const int item = blockIdx.x;
     const int cb = item % p.ncb, rest = item / p.ncb, rc = rest % p.nrc, plane = rest / p.nrc;
@@ -542,29 +558,54 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
     size_t roff = (size_t)lrow * p.nc;
     int to_wrap = p.nr - lrow;
 
+    // Coefficient rows travel global -> shared -> registers.  Each lane prefetches ITS OWN two columns of A, H, V, D
+    // DEPTH rows ahead with 8-byte cp.async copies into a private 32-byte cell per ring row, and later reads the same
+    // cell back: the ring is a latency buffer (DEPTH KB per warp in flight), nothing in it is shared between lanes, so
+    // it needs no barrier -- only cp.async group accounting (one group per row, empty past the chunk's last row).
+    const unsigned ring_s = smem_u32(smem_inv) + (unsigned)G::TILEB + 8 * lane;
+    const float* ring_g = reinterpret_cast<const float*>(smem_inv + G::TILEB) + 2 * lane;
+    const int total_rows = nm + WIN - 1;      // coefficient rows this chunk consumes
+    int issued = 0;
+    auto issue_row = [&]() {                  // row `issued` of the chunk -> ring slot issued % RS
+        if (issued < total_rows) {
+            const unsigned dst = ring_s + (issued % G::RS) * G::ROWB;
+            cp_async8(dst, pA + roff);
+            cp_async8(dst + 256, pH + roff);
+            cp_async8(dst + 512, pV + roff);
+            cp_async8(dst + 768, pD + roff);
+            roff += p.nc;
+            if (--to_wrap == 0) {
+                roff = 0;
+                to_wrap = p.nr;
+            }
+        }
+        cp_async_commit();
+        issued++;
+    };
     u64 wA[NSLOT], wH[NSLOT], wV[NSLOT], wD[NSLOT];  // register window, slot = (row index within the chunk) % NSLOT
-    auto load_row = [&](const int slot) {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(pA + roff));
-        const float2 h = __ldg(reinterpret_cast<const float2*>(pH + roff));
-        const float2 v = __ldg(reinterpret_cast<const float2*>(pV + roff));
-        const float2 d = __ldg(reinterpret_cast<const float2*>(pD + roff));
+    int fetched = 0;
+    auto load_row = [&](const int slot) {      // row `fetched` of the chunk: ring -> register window, then refill
+        cp_async_wait<G::DEPTH - 1>();        // all but the newest DEPTH-1 groups have landed: row `fetched` is there
+        const float* c = ring_g + (fetched % G::RS) * (G::ROWB / 4);
+        const float2 a = *reinterpret_cast<const float2*>(c);
+        const float2 h = *reinterpret_cast<const float2*>(c + 64);
+        const float2 v = *reinterpret_cast<const float2*>(c + 128);
+        const float2 d = *reinterpret_cast<const float2*>(c + 192);
         wA[slot] = pack2(a.x, a.y);
         wH[slot] = pack2(h.x, h.y);
         wV[slot] = pack2(v.x, v.y);
         wD[slot] = pack2(d.x, d.y);
-        roff += p.nc;
-        if (--to_wrap == 0) {
-            roff = 0;
-            to_wrap = p.nr;
-        }
+        fetched++;
+        issue_row();
     };
 #pragma unroll
     for (int i = 0; i < NSLOT; i++) wA[i] = wH[i] = wV[i] = wD[i] = 0ull;
     pdl_launch_dependents();
     pdl_wait();        // the previous level's kernel (or whatever wrote the coefficients) has completed
+#pragma unroll 1
+    for (int i = 0; i < G::DEPTH; i++) issue_row();
 #pragma unroll
-    for (int i = 0; i < WIN + G::PF - 1; i++)
-        if (i < nm + WIN - 1) load_row(i);
+    for (int i = 0; i < WIN; i++) load_row(i);
 
     // ---- row synthesis side: lanes 0..LPR-1 take the even output row, lanes 16..16+LPR-1 the odd one; each turns 4
     // coefficient columns into 8 pixels
@@ -584,7 +625,7 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
 #pragma unroll
         for (int sb = 0; sb < NSLOT; sb++) {  // body: NSLOT output row pairs; all register indices static
             if (s >= nm) return;
-            if (s + G::PF < nm) load_row((sb + NSLOT - 1) % NSLOT);   // the row that pair s + PF adds to the window
+            if (s + 1 < nm) load_row((sb + NSLOT - 1) % NSLOT);   // the row that the next pair adds to the window
             // column synthesis, w_kern_inverse_pass1 (separable.cu:246-289): t1 = IL_y(A) + IH_y(H), t2 = IL_y(V) + IH_y(D)
 #pragma unroll
             for (int par = 0; par < 2; par++) {
@@ -666,7 +707,12 @@ static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2
     const long long nitems = (long long)p.ncb * p.nrc * batch;
     if (nitems > 0x7fffffff) return 0;
     PDWT_PROF(prof_tag("k_inv2d_stream", Mr, Mc), s);
-    PDWT_CUDA(launch_pdl(k_inv2d_stream<HLEN>, (unsigned)nitems, 32, 0, s, p));
+    static bool configured = false;
+    if (!configured) {
+        PDWT_CUDA(cudaFuncSetAttribute(k_inv2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        configured = true;
+    }
+    PDWT_CUDA(launch_pdl(k_inv2d_stream<HLEN>, (unsigned)nitems, 32, G::SMEM, s, p));
     PDWT_LAUNCH_CHECK();
     return 1;
 }
