@@ -166,6 +166,10 @@ int pdwt_wavelets_set_filters_forward(pdwt_wavelets* w, const char* name, unsign
 int pdwt_wavelets_set_filters_inverse(pdwt_wavelets* w, const float* lo, const float* hi); /* wt.cu:585 */
 int pdwt_wavelets_sync(pdwt_wavelets* w);                          /* cudaStreamSynchronize of the object's stream */
 int pdwt_wavelets_set_stream(pdwt_wavelets* w, void* stream);
+/* on != 0: get_image / set_image / get_coeff / set_coeff only enqueue their host<->device copies on the object's
+ * stream (use pinned host memory and pdwt_wavelets_sync before touching it); several objects on different streams
+ * then overlap H2D, kernels and D2H.  Default 0 = the reference's blocking copies (wt.cu:421-434). */
+int pdwt_wavelets_set_async(pdwt_wavelets* w, int on);
 
 /* public data members of the class, wt.h:24-33 */
 int pdwt_wavelets_state(const pdwt_wavelets* w);

@@ -45,6 +45,9 @@ class Wavelets {
     int batch;         // independent planes handled by every method (1 = the reference's behaviour)
     int last_error;    // pdwt_status of the most recent failing call (0 if none)
     void* stream;      // cudaStream_t all work is enqueued on (NULL = legacy default stream)
+    int async_copies;  // 1: get_image/set_image/get_coeff/set_coeff only ENQUEUE their host copies on `stream` (pinned
+                       // host memory; the caller synchronises) so that objects on different streams pipeline
+                       // H2D / kernels / D2H.  0 = the reference's blocking behaviour (wt.cu:421-434)
 
     Wavelets();
     Wavelets(DTYPE* img, int Nr, int Nc, const char* wname, int levels, int memisonhost = 1, int do_separable = 1,

@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
     L.pdwt_wavelets_set_filters_forward.argtypes = [vp, C.c_char_p, C.c_uint, _fp, _fp]
     L.pdwt_wavelets_set_filters_inverse.argtypes = [vp, _fp, _fp]
     L.pdwt_wavelets_set_stream.argtypes = [vp, vp]
+    L.pdwt_wavelets_set_async.argtypes = [vp, ci]
     L.pdwt_wavelets_info.argtypes = [vp]
     L.pdwt_wavelets_info.restype = WInfo
     L.pdwt_wavelets_wname.argtypes = [vp]
@@ -266,6 +267,11 @@ class Wavelets:
         """cudaStream_t (int) or torch.cuda.Stream all subsequent work is enqueued on"""
         s = getattr(stream, "cuda_stream", stream)
         _check(self._L.pdwt_wavelets_set_stream(self._h, C.c_void_p(int(s) if s else None)), "set_stream")
+
+    def set_async(self, on: bool = True):
+        """host copies of get_image/set_image/get_coeff/set_coeff are only enqueued on the object's stream (pinned host
+        memory, call sync() before touching it): objects on different streams pipeline H2D / kernels / D2H"""
+        _check(self._L.pdwt_wavelets_set_async(self._h, 1 if on else 0), "set_async")
 
     def sync(self):
         _check(self._L.pdwt_wavelets_sync(self._h), "pdwt_wavelets_sync")

@@ -77,6 +77,14 @@ static int path_cap()
     if (e && !strcmp(e, "fused")) return 1;
     return 2;
 }
+// Levels with at most this many output pixels (x batch) go to the tile kernels even when the streaming family could
+// take them: a streaming warp needs hlen/2-1 row pairs of warm-up plus its chunk, serially, which is all latency when
+// the whole level is a few hundred thousand pixels (PDWT_SMALL_PX overrides; 0 = always stream).
+static long long small_level_px()
+{
+    const char* e = getenv("PDWT_SMALL_PX");   // read per call: the tests switch it inside one process
+    return e ? atoll(e) : 0;
+}
 }  // namespace pdwt
 
 extern "C" {
@@ -300,7 +308,7 @@ int fwd_sep_2d(const Ctx& x)
         for (int l = 0; l < L; l++) {
             Plane2 dstA = lands_in_c0(L, l) ? x.coeff(0) : x.scratch();
             int done = 0;
-            if (cap >= 2)
+            if (cap >= 2 && (long long)half_up(Nr) * half_up(Nc) * x.batch > small_level_px())
                 TRY(done = s_dwt2_fwd_level(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3),
                                             Nr, Nc, x.batch, x.s));
             if (!done)
@@ -336,7 +344,7 @@ int inv_sep_2d(const Ctx& x)
             const int Mr = level_size(x.w.Nr, l, 0), Mc = level_size(x.w.Nc, l, 0);
             Plane2 dst = (l == 0) ? x.image() : (cur_is_c0 ? x.scratch() : x.coeff(0));
             int done = 0;
-            if (cap >= 2)
+            if (cap >= 2 && (long long)half_up(Mr) * half_up(Mc) * x.batch > small_level_px())
                 TRY(done = s_dwt2_inv_level(x.t, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), dst,
                                             half_up(Mr), half_up(Mc), Mr, Mc, x.batch, x.s));
             if (!done)

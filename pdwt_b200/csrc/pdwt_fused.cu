@@ -54,7 +54,7 @@ struct FwdCfg {
     static constexpr int NV = (SH + 6 + HLEN + 3) / 4;  // vectors one row-pass task reads (4 outputs)
     static constexpr int INP = odd_quad_pitch((INW4 * 4 > 2 * TW - 8 + NV * 4) ? INW4 * 4 : 2 * TW - 8 + NV * 4);
     static constexpr int MP = odd_quad_pitch(TW);     // pitch of S_lo / S_hi
-    static constexpr int RPT = 4;                     // output rows per column-pass task
+    static constexpr int RPT = TH >= 32 ? 4 : 2;      // output rows per column-pass task
     static constexpr size_t SMEM = sizeof(float) * ((size_t)INR * INP + 2 * (size_t)INR * MP);
     static_assert(TH % RPT == 0 && TW % 16 == 0, "tile shape");
 };
@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
     src += (size_t)blockIdx.z * s_src;
     const int x_al = 2 * gx0 - K::C - K::SH;  // multiple of 4
     const int y_0 = 2 * gy0 - K::C;
+    pdl_wait();   // the kernel that wrote `src` (previous level) has completed
 
     // ---- stage the input tile, folding the periodic / odd-size extension (separable.cu:114-121) while loading
     const bool fast = ((Nc & 3) == 0) && x_al >= 0 && (x_al + K::INW4 * 4 <= Nc) && ((((uintptr_t)src) & 15) == 0);
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
     }
     __syncthreads();
 
+    pdl_launch_dependents();   // only the column pass and the stores are left
     // ---- column pass (w_kern_forward_pass2, separable.cu:135-176): A = L_y(lo), H = H_y(lo), V = L_y(hi), D = H_y(hi)
     {
         constexpr int QN = TW / 4, RG = TH / K::RPT;
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
     const int y_0 = cy0 - K::CC;
     const float* srcs[4] = {A + (size_t)blockIdx.z * s_a, H + (size_t)blockIdx.z * s_d, V + (size_t)blockIdx.z * s_d,
                             D + (size_t)blockIdx.z * s_d};
+    pdl_wait();   // the kernel that wrote the coefficients (previous level) has completed
 
     // ---- stage the four coefficient tiles with the single periodic wrap of separable.cu:265-273
     const bool fast = ((nc & 3) == 0) && x_al >= 0 && (x_al + K::INW4 * 4 <= nc) &&
@@ -284,6 +287,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
     }
     __syncthreads();
 
+    pdl_launch_dependents();   // only the row synthesis and the stores are left
     // ---- row synthesis (w_kern_inverse_pass2, separable.cu:293-328): img = IL_x(t1) + IH_x(t2).  A task produces 8
     // consecutive outputs of one row; output k has hl = (k+SHIFT)/2, off = 1 - ((k+SHIFT)&1).
     {
@@ -329,11 +333,20 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
 }
 
 // ================================================================================================ launchers
-template <int HLEN>
-static int launch_fwd(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
-                      cudaStream_t s)
+// Two tile shapes per direction.  The large tile (64 x 32 outputs, 2 CTAs/SM) has the smaller halo; the small tile
+// (32 x 16 outputs, ~27 KB of shared memory, 4+ CTAs/SM) is for levels with so few pixels that a grid of large tiles
+// would leave most SMs idle: there latency, not traffic, is the cost (PDWT_FUSED_TILE=0|1 forces one of them).
+static int tile_choice(long long outputs)
 {
-    constexpr int TW = 64, TH = 32;
+    const char* e = getenv("PDWT_FUSED_TILE");
+    if (e && *e) return atoi(e) != 0;
+    return outputs < 2LL * 148 * 64 * 32 * 4 ? 1 : 0;   // fewer than ~4 waves of large tiles
+}
+
+template <int HLEN, int TW, int TH>
+static int launch_fwd_t(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+                        cudaStream_t s)
+{
     using K = FwdCfg<HLEN, TW, TH>;
     static bool configured = false;
     if (!configured) {
@@ -342,17 +355,24 @@ static int launch_fwd(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, P
     }
     dim3 grid(idiv_up(half_up(Nc), TW), idiv_up(half_up(Nr), TH), batch);
     PDWT_PROF(prof_tag("k_fwd2d", Nr, Nc), s);
-    k_fwd2d<HLEN, TW, TH><<<grid, kFusedThreads, K::SMEM, s>>>(t, src.p, src.stride, A.p, A.stride, H.p, V.p, D.p,
-                                                               H.stride, Nr, Nc);
+    PDWT_CUDA(launch_pdl(k_fwd2d<HLEN, TW, TH>, grid, kFusedThreads, K::SMEM, s, t, (const float*)src.p, src.stride, A.p,
+                         A.stride, H.p, V.p, D.p, H.stride, Nr, Nc));
     PDWT_LAUNCH_CHECK();
     return 1;
 }
-
 template <int HLEN>
-static int launch_inv(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
-                      int batch, cudaStream_t s)
+static int launch_fwd(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+                      cudaStream_t s)
 {
-    constexpr int TWC = 64, THC = 32;
+    if (tile_choice((long long)half_up(Nr) * half_up(Nc) * batch))
+        return launch_fwd_t<HLEN, 32, 16>(t, src, A, H, V, D, Nr, Nc, batch, s);
+    return launch_fwd_t<HLEN, 64, 32>(t, src, A, H, V, D, Nr, Nc, batch, s);
+}
+
+template <int HLEN, int TWC, int THC>
+static int launch_inv_t(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
+                        int batch, cudaStream_t s)
+{
     using K = InvCfg<HLEN, TWC, THC>;
     static bool configured = false;
     if (!configured) {
@@ -361,10 +381,19 @@ static int launch_inv(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Pla
     }
     dim3 grid(idiv_up(nc, TWC), idiv_up(nr, THC), batch);
     PDWT_PROF(prof_tag("k_inv2d", Mr, Mc), s);
-    k_inv2d<HLEN, TWC, THC><<<grid, kFusedThreads, K::SMEM, s>>>(t, A.p, A.stride, H.p, V.p, D.p, H.stride, dst.p,
-                                                                 dst.stride, nr, nc, Mr, Mc);
+    PDWT_CUDA(launch_pdl(k_inv2d<HLEN, TWC, THC>, grid, kFusedThreads, K::SMEM, s, t, (const float*)A.p, A.stride,
+                         (const float*)H.p, (const float*)V.p, (const float*)D.p, H.stride, dst.p, dst.stride, nr, nc, Mr,
+                         Mc));
     PDWT_LAUNCH_CHECK();
     return 1;
+}
+template <int HLEN>
+static int launch_inv(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
+                      int batch, cudaStream_t s)
+{
+    if (tile_choice((long long)nr * nc * batch))
+        return launch_inv_t<HLEN, 32, 16>(t, A, H, V, D, dst, nr, nc, Mr, Mc, batch, s);
+    return launch_inv_t<HLEN, 64, 32>(t, A, H, V, D, dst, nr, nc, Mr, Mc, batch, s);
 }
 
 #define PDWT_HLEN_SWITCH(fn, ...)                   \

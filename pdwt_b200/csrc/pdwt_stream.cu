@@ -109,32 +109,6 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 
 constexpr int round4(int n) { return (n + 3) & ~3; }
 
-// Programmatic dependent launch: the level kernels of one transform are queued back to back on one stream; each lets
-// its successor's CTAs start (launch latency, barrier init, address set-up) while it is still draining, and blocks
-// at pdl_wait() until its predecessor has completed and flushed before touching global memory.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-template <typename Kern, typename Params>
-static cudaError_t launch_pdl(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t s, const Params& p)
-{
-    // measured on B200 (C2): overlapping the next level's launch this way costs ~6% (its CTAs hold shared memory and
-    // registers while they spin), so it is off unless PDWT_PDL=1
-    static const bool no_pdl = getenv("PDWT_PDL") == nullptr;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(grid, 1, 1);
-    cfg.blockDim = dim3(block, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kern, p);
-}
-
 // One lane of the (converged) warp, chosen by the hardware; ptxas keeps the guarded block uniform, so the bulk copies
 // inside compile to a single UBLKCP each instead of a per-lane loop.
 __device__ __forceinline__ bool elect_one()
@@ -195,6 +169,7 @@ struct FwdParams {
     int TH;                  // output rows per chunk
     int ncg, nrc;            // column groups (NCW strips each), row chunks; grid = ncg * nrc * batch CTAs
     int use_tm;
+    int pdl_early;           // PDWT_PDL=1: let the next kernel's CTAs in as soon as this one has started
 };
 
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm, int x, int y, int z, unsigned bar)
@@ -236,7 +211,7 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();   // the only block-wide barrier: after it the warps only meet through mbarriers
-    pdl_launch_dependents();
+    if (p.pdl_early) pdl_launch_dependents();
     pdl_wait();        // the previous level's kernel (or whatever wrote `src`) has completed
 
     if (warp == NCW) {
@@ -359,6 +334,7 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
             const char* rowa = lane_ring + soff + pin * (2 * G::WW * 4);
             load_row(xb, rowa + G::WW * 4);
             const bool more = q + 1 < npairs;
+            if (!more) pdl_launch_dependents();   // last row pair of this warp: the next kernel may start its prologue
             const bool last_in_ss = pin == SR / 2 - 1;
             unsigned nsoff = soff + G::SSB, nbar = bar + 16, nparity = parity;
             if (nsoff == NSS * G::SSB) {
@@ -471,10 +447,11 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
     if (const char* e = getenv("PDWT_TH")) TH = atoi(e) > 0 ? atoi(e) : TH;
     p.TH = TH;
     p.nrc = idiv_up(nr, TH);
+    p.pdl_early = pdl_mode() == 1;
     const long long nctas = (long long)p.ncg * p.nrc * batch;
     if (nctas > 0x7fffffff) return 0;
     PDWT_PROF(prof_tag("k_fwd2d_stream", Nr, Nc), s);
-    PDWT_CUDA(launch_pdl(k_fwd2d_stream<HLEN>, (unsigned)nctas, G::THREADS, G::SMEM, s, p));
+    PDWT_CUDA(launch_pdl(k_fwd2d_stream<HLEN>, dim3((unsigned)nctas), G::THREADS, G::SMEM, s, p));
     PDWT_LAUNCH_CHECK();
     return 1;
 }
@@ -514,6 +491,7 @@ struct InvParams {
     int nr, nc, Mr, Mc;                      // coefficient and output plane sizes (Mr = 2 nr, Mc = 2 nc)
     int TM;                                  // output row PAIRS per chunk
     int ncb, nrc;
+    int pdl_early;
 };
 
 // shared-memory position (in 16-byte chunks) of chunk q of a tile row: XOR swizzle so that both the writers (lane ->
@@ -600,7 +578,7 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
     };
 #pragma unroll
     for (int i = 0; i < NSLOT; i++) wA[i] = wH[i] = wV[i] = wD[i] = 0ull;
-    pdl_launch_dependents();
+    if (p.pdl_early) pdl_launch_dependents();
     pdl_wait();        // the previous level's kernel (or whatever wrote the coefficients) has completed
 #pragma unroll 1
     for (int i = 0; i < G::DEPTH; i++) issue_row();
@@ -625,6 +603,7 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
 #pragma unroll
         for (int sb = 0; sb < NSLOT; sb++) {  // body: NSLOT output row pairs; all register indices static
             if (s >= nm) return;
+            if (s + 1 >= nm) pdl_launch_dependents();
             if (s + 1 < nm) load_row((sb + NSLOT - 1) % NSLOT);   // the row that the next pair adds to the window
             // column synthesis, w_kern_inverse_pass1 (separable.cu:246-289): t1 = IL_y(A) + IH_y(H), t2 = IL_y(V) + IH_y(D)
 #pragma unroll
@@ -704,6 +683,7 @@ static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2
     if (const char* e = getenv("PDWT_TM")) TM = atoi(e) > 0 ? atoi(e) : TM;
     p.TM = TM;
     p.nrc = idiv_up(nr, TM);
+    p.pdl_early = pdl_mode() == 1;
     const long long nitems = (long long)p.ncb * p.nrc * batch;
     if (nitems > 0x7fffffff) return 0;
     PDWT_PROF(prof_tag("k_inv2d_stream", Mr, Mc), s);
@@ -712,7 +692,7 @@ static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2
         PDWT_CUDA(cudaFuncSetAttribute(k_inv2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
         configured = true;
     }
-    PDWT_CUDA(launch_pdl(k_inv2d_stream<HLEN>, (unsigned)nitems, 32, G::SMEM, s, p));
+    PDWT_CUDA(launch_pdl(k_inv2d_stream<HLEN>, dim3((unsigned)nitems), 32, G::SMEM, s, p));
     PDWT_LAUNCH_CHECK();
     return 1;
 }

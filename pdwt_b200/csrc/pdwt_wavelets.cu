@@ -30,8 +30,8 @@ static int cuda_rc(cudaError_t e) { return note_cuda(e); }
 
 Wavelets::Wavelets()
     : d_image(NULL), d_coeffs(NULL), d_tmp(NULL), current_shift_r(0), current_shift_c(0), do_separable(1),
-      do_cycle_spinning(0), state(W_INIT), batch(1), last_error(0), stream(NULL), filters(NULL), d_sums(NULL),
-      h_sums(NULL), launches(0)
+      do_cycle_spinning(0), state(W_INIT), batch(1), last_error(0), stream(NULL), async_copies(0), filters(NULL),
+      d_sums(NULL), h_sums(NULL), launches(0)
 {
     memset(wname, 0, sizeof wname);
     memset(&winfos, 0, sizeof winfos);
@@ -73,7 +73,7 @@ Wavelets::Wavelets(DTYPE* img, int Nr, int Nc, const char* name, int levels, int
                    int do_cycle_spinning_, int do_swt, int ndim, int batch_)
     : d_image(NULL), d_coeffs(NULL), d_tmp(NULL), current_shift_r(0), current_shift_c(0), do_separable(do_separable_),
       do_cycle_spinning(do_cycle_spinning_), state(W_INIT), batch(batch_ < 1 ? 1 : batch_), last_error(0), stream(NULL),
-      filters(NULL), d_sums(NULL), h_sums(NULL), launches(0)
+      async_copies(0), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0)
 {
     memset(wname, 0, sizeof wname);
     winfos.Nr = Nr;
@@ -178,7 +178,7 @@ Wavelets::Wavelets(DTYPE* img, int Nr, int Nc, const char* name, int levels, int
 Wavelets::Wavelets(const Wavelets& W)
     : d_image(NULL), d_coeffs(NULL), d_tmp(NULL), current_shift_r(W.current_shift_r), current_shift_c(W.current_shift_c),
       do_separable(W.do_separable), do_cycle_spinning(W.do_cycle_spinning), winfos(W.winfos), state(W.state),
-      batch(W.batch), last_error(0), stream(W.stream), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0)
+      batch(W.batch), last_error(0), stream(W.stream), async_copies(W.async_copies), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0)
 {
     memcpy(wname, W.wname, sizeof wname);
     if (winfos.Nr < 1 || winfos.Nc < 1) return;
@@ -304,13 +304,14 @@ DTYPE Wavelets::norm2sq()
     return res;
 }
 
-// reference wt.cu:421-424 (blocking D2H; the copy is ordered after the object's stream)
+// reference wt.cu:421-424 (blocking D2H; the copy is ordered after the object's stream).  With async_copies set the
+// call only enqueues the copy: `img` (pinned) is valid after the caller synchronises the stream.
 int Wavelets::get_image(DTYPE* img)
 {
     if (!d_image || !img) return 0;
     const size_t n = (size_t)winfos.Nr * winfos.Nc * batch;
     int rc = cuda_rc(cudaMemcpyAsync(img, d_image, sizeof(DTYPE) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    if (rc == PDWT_OK) rc = cuda_rc(cudaStreamSynchronize((cudaStream_t)stream));
+    if (rc == PDWT_OK && !async_copies) rc = cuda_rc(cudaStreamSynchronize((cudaStream_t)stream));
     if (rc < 0) {
         last_error = rc;
         return 0;
@@ -326,7 +327,7 @@ void Wavelets::set_image(DTYPE* img, int mem_is_on_device)
     int rc = cuda_rc(cudaMemcpyAsync(d_image, img, sizeof(DTYPE) * n,
                                      mem_is_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                      (cudaStream_t)stream));
-    if (rc == PDWT_OK && !mem_is_on_device) rc = cuda_rc(cudaStreamSynchronize((cudaStream_t)stream));
+    if (rc == PDWT_OK && !mem_is_on_device && !async_copies) rc = cuda_rc(cudaStreamSynchronize((cudaStream_t)stream));
     if (rc < 0) last_error = rc;
     if (state != W_CREATION_ERROR) state = W_INIT;
 }
@@ -346,7 +347,7 @@ static int copy_coeff(Wavelets* W, DTYPE* host_or_dev, int num, cudaMemcpyKind k
     else
         e = cudaMemcpy2DAsync(host_or_dev, n * sizeof(DTYPE), W->d_coeffs[num], stride * sizeof(DTYPE), n * sizeof(DTYPE),
                               W->batch, kind, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && !W->async_copies) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
         W->last_error = note_cuda(e);
         return 0;
@@ -545,6 +546,12 @@ int pdwt_wavelets_set_stream(pdwt_wavelets* w, void* stream)
 {
     CHECK_W;
     w->W.stream = stream;
+    return PDWT_OK;
+}
+int pdwt_wavelets_set_async(pdwt_wavelets* w, int on)
+{
+    CHECK_W;
+    w->W.async_copies = on ? 1 : 0;
     return PDWT_OK;
 }
 int pdwt_wavelets_state(const pdwt_wavelets* w) { return w ? (int)w->W.state : (int)W_CREATION_ERROR; }

@@ -253,3 +253,54 @@ def test_custom_filters_cdf97_like():
     W.inverse(); R.inverse()
     assert bitexact(W.get_image(), R.get_image())
     assert W.set_filters_forward("toolong", np.zeros(41, np.float32), np.zeros(41, np.float32)) == -1
+
+
+@pytest.mark.parametrize("env", [{"PDWT_SMALL_PX": "100000000"}, {"PDWT_SMALL_PX": "70000"},
+                                 {"PDWT_PATH": "fused", "PDWT_FUSED_TILE": "0"}, {"PDWT_PATH": "fused", "PDWT_FUSED_TILE": "1"},
+                                 {"PDWT_PDL": "1"}, {"PDWT_PDL": "2"}, {"PDWT_PDL": "2", "PDWT_SMALL_PX": "70000"}],
+                         ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
+def test_dispatch_switches_do_not_change_a_bit(env, monkeypatch):
+    """per-level family choice (stream for large levels, tile kernels for small ones), both tile shapes and the
+    programmatic-dependent-launch modes are scheduling decisions: results stay bit-identical to the oracle"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for shape, wname, levels in (((1024, 768), "db7", 3), ((520, 776), "db4", 3), ((512, 1280), "sym8", 2)):
+        x = rnd(shape, 21)
+        W = Wavelets(x, wname, levels)
+        O = oracle.Wavelets(x, wname, levels)
+        for _ in range(2):                      # twice: back-to-back launches exercise the dependent-launch chain
+            W.set_image(x)
+            W.forward()
+        O.forward()
+        for i in range(W.ncoeffs):
+            assert bitexact(W.get_coeff(i), O.get_coeff(i)), (env, shape, i)
+        W.inverse(); O.inverse()
+        assert bitexact(W.get_image(), O.get_image()), (env, shape)
+
+
+def test_async_copies_pipeline_over_streams():
+    """set_async(True): host copies are only enqueued on the object's stream; several objects on their own streams
+    overlap H2D / kernels / D2H and still deliver exactly the blocking result"""
+    import torch
+    xs = [rnd((512, 640), 40 + i) for i in range(3)]
+    ref = []
+    for x in xs:
+        W = Wavelets(x, "db7", 3)
+        W.forward(); W.soft_threshold(5.0); W.inverse()
+        ref.append(W.get_image())
+    h_in = [torch.from_numpy(x).pin_memory() for x in xs]
+    h_out = [torch.empty((512, 640), dtype=torch.float32).pin_memory() for _ in xs]
+    Ws = [Wavelets(None, "db7", 3, shape=(512, 640)) for _ in xs]
+    streams = [torch.cuda.Stream() for _ in xs]
+    for W, s in zip(Ws, streams):
+        W.set_stream(s)
+        W.set_async(True)
+    for rep in range(3):
+        for W, a, b in zip(Ws, h_in, h_out):
+            W.set_image(a.numpy())
+            W.forward(); W.soft_threshold(5.0); W.inverse()
+            W.get_image(b.numpy())
+    for W in Ws:
+        W.sync()
+    for b, r in zip(h_out, ref):
+        assert bitexact(b.numpy(), r)
