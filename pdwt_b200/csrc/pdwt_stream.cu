@@ -99,6 +99,21 @@ __device__ __forceinline__ unsigned mbar_test(unsigned bar, unsigned parity)
         : "memory");
     return ok;
 }
+// immediate (never suspending) probe, for polling several barriers in turn
+__device__ __forceinline__ unsigned mbar_poll(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 // global -> shared::cta, `bytes` multiple of 16, both addresses 16-byte aligned; completes on `bar`
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar)
 {
@@ -107,7 +122,30 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only), and its hand-over to an mbarrier
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 constexpr int round4(int n) { return (n + 3) & ~3; }
+
+static int sm_count()
+{
+    static const int n = []() {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) {
+            cudaGetLastError();
+            v = 148;
+        }
+        return v;
+    }();
+    return n;
+}
 
 // One lane of the (converged) warp, chosen by the hardware; ptxas keeps the guarded block uniform, so the bulk copies
 // inside compile to a single UBLKCP each instead of a per-lane loop.
@@ -184,6 +222,22 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+#ifdef PDWT_EXPERIMENTS
+// timeline instrumentation (PDWT_EXPERIMENTS builds only): 8 globaltimer stamps for each of the first 1024 CTAs
+__device__ unsigned long long g_timeline[1024 * 8];
+__device__ __forceinline__ void tl_stamp(int cta, int slot)
+{
+    if (cta < 1024) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_timeline[cta * 8 + slot] = t;
+    }
+}
+#define TL(slot, cond) do { if (cond) tl_stamp(blockIdx.x, slot); } while (0)
+#else
+#define TL(slot, cond) do { } while (0)
+#endif
+
 template <int HLEN>
 __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) k_fwd2d_stream(const __grid_constant__ FwdParams<HLEN> p)
 {
@@ -204,6 +258,7 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
     const int nss = (2 * npairs + SR - 1) / SR;   // super-slots per consumer
     const int vr0 = 2 * y0 - G::C;           // first input row (virtual: < 0 or >= Nr wraps around)
     const int nstrips = min(NCW, (p.nc - cg * NCW * G::WO + G::WO - 1) / G::WO);   // strips of this CTA inside the image
+    TL(0, threadIdx.x == 0);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NCW * NSS * 2; i++) mbar_init(bar_s + 8 * i, 1);
@@ -213,13 +268,14 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
     __syncthreads();   // the only block-wide barrier: after it the warps only meet through mbarriers
     if (p.pdl_early) pdl_launch_dependents();
     pdl_wait();        // the previous level's kernel (or whatever wrote `src`) has completed
+    TL(1, threadIdx.x == 0);
 
     if (warp == NCW) {
         // ===================================================================================== producer warp
         const float* src = p.src + (size_t)plane * p.s_src;
-        for (int k = 0; k < nss; k++) {
+        // super-slot k of strip w -> ring slot k % NSS
+        auto issue = [&](const int k, const int w) {
             const int slot = k % NSS;
-            const unsigned par_e = ((k / NSS) + 1) & 1;   // parity of the consumer's (k/NSS)-th release of this slot
             int row0 = vr0 + SR * k;
             // rows needed from this super-slot all inside the image? (rows past the chunk's last pair may fall outside:
             // the tensor request zero-fills them and nobody reads them)
@@ -227,37 +283,69 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
             const bool rows_in = row0 >= 0 && last_needed < p.Nr;
             row0 += (row0 < 0) ? p.Nr : 0;
             row0 -= (row0 >= p.Nr) ? p.Nr : 0;
-            for (int w = 0; w < nstrips; w++) {
-                const unsigned full = bar_s + 16 * (w * NSS + slot), empty = full + 8;
-                if (k >= NSS) mbar_wait(empty, par_e);
+            const unsigned full = bar_s + 16 * (w * NSS + slot);
+            const int xs = 2 * (cg * NCW + w) * G::WO - G::AL;
+            const unsigned dst = ring_s + (w * NSS + slot) * G::SSB;
+            if (p.use_tm && rows_in && xs >= 0 && xs + G::WW <= p.Nc) {
                 if (elect_one()) {
-                    const int xs = 2 * (cg * NCW + w) * G::WO - G::AL;
-                    const unsigned dst = ring_s + (w * NSS + slot) * G::SSB;
                     mbar_expect_tx(full, G::SSB);
-                    if (p.use_tm && rows_in && xs >= 0 && xs + G::WW <= p.Nc) {
-                        tma_load_3d(dst, &p.tm, xs, vr0 + SR * k, plane, full);
-                    } else {
-                        // periodic extension (separable.cu:114-121, even sizes): wrapped row index, and a second
-                        // copy for the columns that wrap around the image
-                        const int x_lo = max(xs, 0), x_hi = min(xs + G::WW, p.Nc);
-                        const unsigned main_dst = (x_lo - xs) * 4, main_bytes = (x_hi - x_lo) * 4;
-                        const int wrap_src = (xs < 0) ? p.Nc + xs : 0;
-                        const unsigned wrap_dst = (xs < 0) ? 0 : (p.Nc - xs) * 4;
-                        const unsigned wrap_bytes =
-                            (xs < 0) ? -xs * 4 : ((xs + G::WW > p.Nc) ? (xs + G::WW - p.Nc) * 4 : 0);
-                        int row = row0;
-#pragma unroll 1
-                        for (int r = 0; r < SR; r++) {
-                            const float* g = src + (size_t)row * p.Nc;
-                            bulk_g2s(dst + r * G::WW * 4 + main_dst, g + x_lo, main_bytes, full);
-                            if (wrap_bytes) bulk_g2s(dst + r * G::WW * 4 + wrap_dst, g + wrap_src, wrap_bytes, full);
-                            row = (row + 1 == p.Nr) ? 0 : row + 1;
-                        }
+                    tma_load_3d(dst, &p.tm, xs, vr0 + SR * k, plane, full);
+                }
+            } else {
+                // periodic extension (separable.cu:114-121, even sizes): every lane copies 16-byte pieces with a
+                // wrapped row and column index (xs, Nc and WW are multiples of 4, so a piece never straddles the
+                // wrap), then hands its copies to the barrier.  LDGSTS instead of per-row bulk copies: a bulk copy
+                // costs the issuing warp ~120 cycles and an edge super-slot would need 16 of them.
+                constexpr int CPR = G::WW / 4;   // pieces per row
+                constexpr int NIT = (SR * CPR + 31) / 32;
+                const float* g[NIT];
+#pragma unroll
+                for (int it = 0; it < NIT; it++) {   // all addresses first, then the copies back to back
+                    const int i = lane + 32 * it;
+                    const int r = i / CPR, c = i - r * CPR;
+                    int row = row0 + r;
+                    row -= (row >= p.Nr) ? p.Nr : 0;
+                    int x = xs + 4 * c;
+                    x += (x < 0) ? p.Nc : 0;
+                    x -= (x >= p.Nc) ? p.Nc : 0;
+                    g[it] = src + (size_t)row * p.Nc + x;
+                }
+#pragma unroll
+                for (int it = 0; it < NIT; it++)
+                    if (lane + 32 * it < SR * CPR) cp_async16(dst + (lane + 32 * it) * 16, g[it]);
+                cp_async_mbar_arrive(full);   // +1 pending now, -1 when this lane's copies have landed
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full);   // the barrier's own count of 1
+            }
+            __syncwarp();
+        };
+        // Round-robin over the strips: a strip is served as soon as ITS consumer has handed the ring slot back, so one
+        // slow consumer does not hold up the refills of the others (the consumers of a CTA drift apart by whole pairs).
+        int next[NCW];
+#pragma unroll
+        for (int w = 0; w < NCW; w++) next[w] = 0;
+        int remaining = nstrips * nss;
+        while (remaining > 0) {
+            bool any = false;
+#pragma unroll
+            for (int w = 0; w < NCW; w++) {
+                const int k = next[w];
+                if (w < nstrips && k < nss) {
+                    unsigned ok = 1;
+                    if (k >= NSS)   // parity of the consumer's (k/NSS)-th release of this slot
+                        ok = mbar_poll(bar_s + 16 * (w * NSS + k % NSS) + 8, ((k / NSS) + 1) & 1);
+                    if (__shfl_sync(0xffffffffu, ok, 0)) {
+                        issue(k, w);
+                        next[w] = k + 1;
+                        remaining--;
+                        any = true;
                     }
                 }
-                __syncwarp();
             }
+            TL(2, lane == 0 && next[0] == 1 && remaining == nstrips * (nss - 1));
+            if (!any) __nanosleep(40);
         }
+        TL(7, lane == 0);
         return;
     }
 
@@ -327,6 +415,7 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
     unsigned soff = 0, bar = my_bar, parity = 0;  // ring position (byte offset, full barrier, phase) of the super-slot
     float xa[G::NV * 4], xb[G::NV * 4];
     mbar_wait(bar, parity);
+    TL(3, threadIdx.x == 0);
     load_row(xa, lane_ring);
     for (;;) {
 #pragma unroll
@@ -351,6 +440,8 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar + 8);
             }
+            TL(4, q == 0 && threadIdx.x == 0);
+            TL(5, q == H2 - 1 && threadIdx.x == 0);
             // the output row that received its last tap (j = hlen-1) in this pair
             if (q >= H2 - 1) {
                 const int sl = (sb + 1) % H2;
@@ -367,7 +458,10 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
                 }
                 oA += p.nc; oH += p.nc; oV += p.nc; oD += p.nc;
             }
-            if (!more) return;
+            if (!more) {
+                TL(6, threadIdx.x == 0);
+                return;
+            }
             q++;
             if (last_in_ss) {
                 if (!ready) mbar_wait(nbar, nparity);
@@ -413,10 +507,13 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
     if ((((uintptr_t)src.p) & 15) || (src.stride & 3)) return 0;
     if ((((uintptr_t)A.p | (uintptr_t)H.p | (uintptr_t)V.p | (uintptr_t)D.p) & 7) || (A.stride & 1) || (H.stride & 1))
         return 0;
-    static bool configured = false;
-    if (!configured) {
+    static int per_sm = 0;   // resident CTAs per SM
+    if (!per_sm) {
         PDWT_CUDA(cudaFuncSetAttribute(k_fwd2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        configured = true;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd2d_stream<HLEN>, G::THREADS, G::SMEM) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 3;
+        }
     }
     FwdParams<HLEN> p;
     memset(&p.tm, 0, sizeof p.tm);
@@ -440,10 +537,27 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
     p.s_src = src.stride; p.s_a = A.stride; p.s_d = H.stride;
     p.Nr = Nr; p.Nc = Nc; p.nr = nr; p.nc = nc;
     p.ncg = idiv_up(nc, G::WO * G::NCW);
-    // chunk height: the largest power of two in [8, 64] that still yields ~1.5 consumer warps per SM sub-partition
-    // (148 x 4 of them); the vertical halo costs hlen-2 input rows of row-pass work per chunk
+    // Chunk height.  A CTA (NCW strips x TH output rows) costs TH + hlen/2 - 1 row pairs per consumer warp (the vertical
+    // halo is row-pass work only, but the scatter accumulators need the same warm-up), an SM holds up to 4 CTAs and
+    // works through the pairs of its resident warps at a roughly constant rate, so the kernel ends when the busiest SM
+    // does: minimise (CTAs on the busiest SM) x (pairs per CTA).  For one 4096^2 image that picks TH = 56 (296 CTAs = 2
+    // per SM) instead of a power of two that leaves 40 SMs with half the work of the others.
     int TH = 64;
-    while (TH > 8 && (long long)idiv_up(nc, G::WO) * idiv_up(nr, TH) * batch < 900) TH >>= 1;
+    {
+        const int sms = sm_count();
+        double best = 1e30;
+        for (int th = 128; th >= 4; th -= 2) {
+            const long long ctas = (long long)p.ncg * idiv_up(nr, th) * batch;
+            const long long full = ctas / ((long long)sms * per_sm), rest = ctas % ((long long)sms * per_sm);
+            const double units = (double)(full * per_sm + (rest + sms - 1) / sms) * (th + G::H2 - 1);
+            // prefer at least two CTAs per SM when it is nearly free: a lone warp per scheduler hides no latency
+            const double cost = units * (ctas <= sms ? 1.15 : 1.0);
+            if (cost < best * 0.999) {
+                best = cost;
+                TH = th;
+            }
+        }
+    }
     if (const char* e = getenv("PDWT_TH")) TH = atoi(e) > 0 ? atoi(e) : TH;
     p.TH = TH;
     p.nrc = idiv_up(nr, TH);
@@ -468,17 +582,24 @@ struct InvGeom {
     static constexpr int SHIFT = (H2 & 1) ? 0 : 1;
     static constexpr int WIN = H2 + SHIFT;              // coefficient rows (columns) behind one output pair
     static constexpr int NSLOT = WIN + 1;               // register window: WIN rows + the row being pulled from the ring
+    static constexpr int UNR = NSLOT * (NSLOT >= 7 ? 1 : 2);  // row pairs per unrolled loop body (even, >= 8)
+    static constexpr int RS = UNR;                      // ring slots = the unroll period, so every ring address is static
     static constexpr int DEPTH = 7;                     // coefficient rows in flight global -> shared (cp.async groups)
-    static constexpr int RS = DEPTH + 1;                // ring slots (one more than in flight: never refill the slot just read)
     static constexpr int ROWB = 4 * 64 * 4;             // ring bytes per coefficient row: A,H,V,D x 64 columns
     static constexpr int ALC = (CC + 1) & ~1;           // the strip starts ALC coefficient columns left of k0 (even)
     static constexpr int SHC = ALC - CC;
     static constexpr int NP = (SHC + WIN + 3 + 1) & ~1; // (t1,t2) pairs a row-synthesis lane reads (4 coefficient columns)
     static constexpr int WOUT = 4 * ((64 - NP) / 4) + 4; // coefficient columns a warp turns into pixels
     static constexpr int LPR = WOUT / 4;                // row-synthesis lanes per output row (<= 16)
-    static constexpr size_t TILEB = 2 * 2 * 64 * 8;     // double-buffered tile: 2 output rows x 64 (t1,t2) pairs
+    // tile row: 32 chunks of 16 bytes (2 (t1,t2) pairs each).  Even chunks sit at positions 0..15, odd chunks at 20..35:
+    // the writers (lane -> chunk lane) and the readers (lane -> chunks 2*lane' + v, i.e. CONSECUTIVE positions
+    // lane' + v/2 in one of the halves) are both bank-conflict free and every offset is a compile-time immediate
+    static constexpr int ODD0 = 20;
+    static constexpr int TROWB = (ODD0 + 16) * 16;      // bytes per tile row
+    static constexpr size_t TILEB = 2 * 2 * TROWB;      // double-buffered tile: 2 output rows
     static constexpr size_t SMEM = TILEB + (size_t)RS * ROWB;
     static_assert(LPR <= 16 && WOUT - 4 + NP <= 64, "row-synthesis window exceeds the strip");
+    static_assert(UNR % 2 == 0 && UNR % NSLOT == 0 && DEPTH < RS, "static ring / tile addressing");
 };
 
 template <int HLEN>
@@ -494,9 +615,6 @@ struct InvParams {
     int pdl_early;
 };
 
-// shared-memory position (in 16-byte chunks) of chunk q of a tile row: XOR swizzle so that both the writers (lane ->
-// chunk lane) and the readers (lane -> chunks 2*lane' + v) are bank-conflict free
-__device__ __forceinline__ int swz(int q) { return q ^ ((q >> 3) & 1); }
 
 // 8-byte asynchronous copy global -> shared (LDGSTS), tracked by cp.async groups
 __device__ __forceinline__ void cp_async8(unsigned dst, const void* src)
@@ -514,9 +632,8 @@ template <int HLEN>
 __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__ InvParams<HLEN> p)
 {
     using G = InvGeom<HLEN>;
-    constexpr int H2 = G::H2, NSLOT = G::NSLOT, WIN = G::WIN, SHIFT = G::SHIFT;
+    constexpr int H2 = G::H2, NSLOT = G::NSLOT, WIN = G::WIN, SHIFT = G::SHIFT, UNR = G::UNR, DEPTH = G::DEPTH;
     extern __shared__ __align__(16) unsigned char smem_inv[];
-    float (*tile)[2][64 * 2] = reinterpret_cast<float (*)[2][64 * 2]>(smem_inv);   // [buffer][output row parity][(t1,t2) x 64]
     const int lane = threadIdx.x;
     const int item = blockIdx.x;
     const int cb = item % p.ncb, rest = item / p.ncb, rc = rest % p.nrc, plane = rest / p.nrc;
@@ -527,61 +644,64 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
     int col = k0 - G::ALC + 2 * lane;
     col += (col < 0) ? p.nc : 0;
     col -= (col >= p.nc) ? p.nc : 0;
-    const float* pA = p.A + (size_t)plane * p.s_a + col;
-    const float* pH = p.Hb + (size_t)plane * p.s_d + col;
-    const float* pV = p.V + (size_t)plane * p.s_d + col;
-    const float* pD = p.D + (size_t)plane * p.s_d + col;
     int lrow = m0 - G::CC;                    // next coefficient row to load (wrapped: separable.cu:265-273)
     lrow += (lrow < 0) ? p.nr : 0;
-    size_t roff = (size_t)lrow * p.nc;
     int to_wrap = p.nr - lrow;
+    // ONE running per-lane pointer (into A) and three uniform byte distances to the same element of H, V, D: per row
+    // that is a 64-bit add for each address and one for the advance, nothing else
+    const char* pa = reinterpret_cast<const char*>(p.A + (size_t)plane * p.s_a + (size_t)lrow * p.nc + col);
+    const ptrdiff_t plane_d = (ptrdiff_t)((size_t)plane * p.s_d) - (ptrdiff_t)((size_t)plane * p.s_a);
+    const ptrdiff_t dH = (reinterpret_cast<const char*>(p.Hb) - reinterpret_cast<const char*>(p.A)) + 4 * plane_d;
+    const ptrdiff_t dV = (reinterpret_cast<const char*>(p.V) - reinterpret_cast<const char*>(p.A)) + 4 * plane_d;
+    const ptrdiff_t dD = (reinterpret_cast<const char*>(p.D) - reinterpret_cast<const char*>(p.A)) + 4 * plane_d;
+    const ptrdiff_t row_b = 4 * (ptrdiff_t)p.nc, wrap_b = 4 * (ptrdiff_t)p.nc * p.nr;
 
     // Coefficient rows travel global -> shared -> registers.  Each lane prefetches ITS OWN two columns of A, H, V, D
     // DEPTH rows ahead with 8-byte cp.async copies into a private 32-byte cell per ring row, and later reads the same
     // cell back: the ring is a latency buffer (DEPTH KB per warp in flight), nothing in it is shared between lanes, so
     // it needs no barrier -- only cp.async group accounting (one group per row, empty past the chunk's last row).
+    // Row r of the chunk lives in ring slot r % RS; RS equals the unroll period of the main loop, so every slot index
+    // below is a compile-time constant.
     const unsigned ring_s = smem_u32(smem_inv) + (unsigned)G::TILEB + 8 * lane;
     const float* ring_g = reinterpret_cast<const float*>(smem_inv + G::TILEB) + 2 * lane;
-    const int total_rows = nm + WIN - 1;      // coefficient rows this chunk consumes
-    int issued = 0;
-    auto issue_row = [&]() {                  // row `issued` of the chunk -> ring slot issued % RS
-        if (issued < total_rows) {
-            const unsigned dst = ring_s + (issued % G::RS) * G::ROWB;
-            cp_async8(dst, pA + roff);
-            cp_async8(dst + 256, pH + roff);
-            cp_async8(dst + 512, pV + roff);
-            cp_async8(dst + 768, pD + roff);
-            roff += p.nc;
+    int rows_left = nm + WIN - 1;             // coefficient rows of this chunk not yet requested
+    auto issue_row = [&](const int slot) {
+        if (rows_left > 0) {
+            const unsigned dst = ring_s + slot * G::ROWB;
+            cp_async8(dst, pa);
+            cp_async8(dst + 256, pa + dH);
+            cp_async8(dst + 512, pa + dV);
+            cp_async8(dst + 768, pa + dD);
+            pa += row_b;
             if (--to_wrap == 0) {
-                roff = 0;
+                pa -= wrap_b;
                 to_wrap = p.nr;
             }
         }
         cp_async_commit();
-        issued++;
+        rows_left--;
     };
     u64 wA[NSLOT], wH[NSLOT], wV[NSLOT], wD[NSLOT];  // register window, slot = (row index within the chunk) % NSLOT
-    int fetched = 0;
-    auto load_row = [&](const int slot) {      // row `fetched` of the chunk: ring -> register window, then refill
-        cp_async_wait<G::DEPTH - 1>();        // all but the newest DEPTH-1 groups have landed: row `fetched` is there
-        const float* c = ring_g + (fetched % G::RS) * (G::ROWB / 4);
+    // row r of the chunk: ring slot r % RS -> window slot r % NSLOT, then request row r + DEPTH
+    auto load_row = [&](const int r) {
+        cp_async_wait<DEPTH - 1>();           // all but the newest DEPTH-1 groups have landed: row r is there
+        const float* c = ring_g + (r % G::RS) * (G::ROWB / 4);
         const float2 a = *reinterpret_cast<const float2*>(c);
         const float2 h = *reinterpret_cast<const float2*>(c + 64);
         const float2 v = *reinterpret_cast<const float2*>(c + 128);
         const float2 d = *reinterpret_cast<const float2*>(c + 192);
-        wA[slot] = pack2(a.x, a.y);
-        wH[slot] = pack2(h.x, h.y);
-        wV[slot] = pack2(v.x, v.y);
-        wD[slot] = pack2(d.x, d.y);
-        fetched++;
-        issue_row();
+        wA[r % NSLOT] = pack2(a.x, a.y);
+        wH[r % NSLOT] = pack2(h.x, h.y);
+        wV[r % NSLOT] = pack2(v.x, v.y);
+        wD[r % NSLOT] = pack2(d.x, d.y);
+        issue_row((r + DEPTH) % G::RS);
     };
 #pragma unroll
     for (int i = 0; i < NSLOT; i++) wA[i] = wH[i] = wV[i] = wD[i] = 0ull;
     if (p.pdl_early) pdl_launch_dependents();
     pdl_wait();        // the previous level's kernel (or whatever wrote the coefficients) has completed
-#pragma unroll 1
-    for (int i = 0; i < G::DEPTH; i++) issue_row();
+#pragma unroll
+    for (int i = 0; i < DEPTH; i++) issue_row(i);
 #pragma unroll
     for (int i = 0; i < WIN; i++) load_row(i);
 
@@ -592,19 +712,18 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
     const bool row_lane = lq < G::LPR;
     float* out = p.dst + (size_t)plane * p.s_dst + (size_t)(2 * m0 + g) * p.Mc + px0;
     const bool st0 = row_lane && px0 + 4 <= p.Mc, st1 = row_lane && px0 + 8 <= p.Mc;
-    int rd_off[G::NP / 2];                    // float offsets of the chunks this lane reads, within one tile row
-#pragma unroll
-    for (int v = 0; v < G::NP / 2; v++) rd_off[v] = 4 * swz((2 * lq + v) & 31);
-    const int wr_off = 4 * swz(lane);
-    int buf = 0;
+    // tile addressing (see InvGeom): the writer stores chunk `lane`, the reader loads chunks 2*lq + v
+    unsigned char* const tile_wr = smem_inv + 16 * ((lane >> 1) + (lane & 1) * G::ODD0);
+    const unsigned char* const tile_rd = smem_inv + g * G::TROWB + 16 * lq;
 
     int s = 0;
     for (;;) {
 #pragma unroll
-        for (int sb = 0; sb < NSLOT; sb++) {  // body: NSLOT output row pairs; all register indices static
+        for (int u = 0; u < UNR; u++) {       // body: UNR output row pairs; register, ring and tile indices all static
             if (s >= nm) return;
             if (s + 1 >= nm) pdl_launch_dependents();
-            if (s + 1 < nm) load_row((sb + NSLOT - 1) % NSLOT);   // the row that the next pair adds to the window
+            if (s + 1 < nm) load_row(u + WIN);   // the row that the NEXT pair adds to the window (one pair of slack)
+            const int sb = u % NSLOT, buf = u & 1;
             // column synthesis, w_kern_inverse_pass1 (separable.cu:246-289): t1 = IL_y(A) + IH_y(H), t2 = IL_y(V) + IH_y(D)
 #pragma unroll
             for (int par = 0; par < 2; par++) {
@@ -621,7 +740,7 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
                 float t1a, t1b, t2a, t2b;
                 unpack2(fadd2(sa, sh), t1a, t1b);
                 unpack2(fadd2(sv, sd), t2a, t2b);
-                *reinterpret_cast<float4*>(&tile[buf][par][wr_off]) = make_float4(t1a, t2a, t1b, t2b);
+                *reinterpret_cast<float4*>(tile_wr + (buf * 2 + par) * G::TROWB) = make_float4(t1a, t2a, t1b, t2b);
             }
             __syncwarp();
             // row synthesis, w_kern_inverse_pass2 (separable.cu:293-328): img = IL_x(t1) + IH_x(t2)
@@ -629,7 +748,8 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
                 u64 tw[G::NP];
 #pragma unroll
                 for (int v = 0; v < G::NP / 2; v++) {
-                    const float4 f = *reinterpret_cast<const float4*>(&tile[buf][g][rd_off[v]]);
+                    const float4 f = *reinterpret_cast<const float4*>(tile_rd + buf * 2 * G::TROWB +
+                                                                      16 * ((v >> 1) + (v & 1) * G::ODD0));
                     tw[2 * v] = pack2(f.x, f.y);
                     tw[2 * v + 1] = pack2(f.z, f.w);
                 }
@@ -649,7 +769,6 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
                 if (st1) *reinterpret_cast<float4*>(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
             }
             out += 2 * (size_t)p.Mc;
-            buf ^= 1;
             s++;
         }
     }
@@ -677,9 +796,31 @@ static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2
     p.s_a = A.stride; p.s_d = H.stride; p.s_dst = dst.stride;
     p.nr = nr; p.nc = nc; p.Mr = Mr; p.Mc = Mc;
     p.ncb = idiv_up(nc, G::WOUT);
-    // chunk height: a chunk re-reads only WIN-1 coefficient rows, so small chunks are cheap; aim at ~4 waves of 12 warps/SM
+    // Chunk height (output row PAIRS per one-warp CTA).  An item costs TM loop iterations plus a prologue worth ~2.5 of
+    // them (WIN-1 extra coefficient rows and the pipeline fill); items are spread over sms x per_sm resident warps, so
+    // the kernel takes about ceil(items / slots) x (TM + 2.5): pick the TM that minimises it (4096^2: TM = 32, exactly
+    // one item per slot).
+    static int per_sm = 0;
+    if (!per_sm) {
+        PDWT_CUDA(cudaFuncSetAttribute(k_inv2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv2d_stream<HLEN>, 32, G::SMEM) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 12;
+        }
+    }
     int TM = 32;
-    while (TM > 4 && (long long)p.ncb * idiv_up(nr, TM) * batch < 148LL * 12 * 2) TM >>= 1;
+    {
+        const long long slots = (long long)sm_count() * per_sm;
+        double best = 1e30;
+        for (int tm = 64; tm >= 2; tm--) {
+            const long long items = (long long)p.ncb * idiv_up(nr, tm) * batch;
+            const double cost = (double)((items + slots - 1) / slots) * (tm + 2.5);
+            if (cost < best * 0.999) {
+                best = cost;
+                TM = tm;
+            }
+        }
+    }
     if (const char* e = getenv("PDWT_TM")) TM = atoi(e) > 0 ? atoi(e) : TM;
     p.TM = TM;
     p.nrc = idiv_up(nr, TM);
@@ -687,15 +828,20 @@ static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2
     const long long nitems = (long long)p.ncb * p.nrc * batch;
     if (nitems > 0x7fffffff) return 0;
     PDWT_PROF(prof_tag("k_inv2d_stream", Mr, Mc), s);
-    static bool configured = false;
-    if (!configured) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_inv2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        configured = true;
-    }
     PDWT_CUDA(launch_pdl(k_inv2d_stream<HLEN>, dim3((unsigned)nitems), 32, G::SMEM, s, p));
     PDWT_LAUNCH_CHECK();
     return 1;
 }
+
+#ifdef PDWT_EXPERIMENTS
+}  // namespace pdwt
+extern "C" int pdwt_debug_timeline(unsigned long long* out, int n)
+{
+    if (n > 1024 * 8) n = 1024 * 8;
+    return (int)cudaMemcpyFromSymbol(out, pdwt::g_timeline, sizeof(unsigned long long) * n);
+}
+namespace pdwt {
+#endif
 
 #define PDWT_STREAM_HLEN_SWITCH(fn, ...)            \
     switch (t.hlen) {                               \
