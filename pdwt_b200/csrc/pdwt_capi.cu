@@ -404,11 +404,32 @@ int inv_sep_1d(const Ctx& x, bool swt)
 }
 
 // ---- separable 2-D SWT (reference buffer plan, separable.cu:496-515 / 629-649) -------------------------------
+// Fused SWT levels ping-pong the approximation between d_coeffs[0] and d_tmp (a level must not overwrite the plane its
+// neighbours' halos still read), arranged so that the last level lands in d_coeffs[0].  The generic two-pass scheme
+// needs all of d_tmp for its row-pass outputs, so the choice is made once per transform: fused only if EVERY level fits.
+bool swt_all_levels_fused(const Ctx& x)
+{
+    if (path_cap() < 1) return false;
+    return w_swt2_supported(x.t, x.w.Nr, x.w.Nc, x.w.nlevels, x.batch) != 0;
+}
+
 int fwd_swt_2d(const Ctx& x)
 {
-    const int Nr = x.w.Nr, Nc = x.w.Nc;
+    const int Nr = x.w.Nr, Nc = x.w.Nc, L = x.w.nlevels;
+    if (swt_all_levels_fused(x)) {
+        Plane2 cur = x.image();
+        for (int l = 0; l < L; l++) {
+            Plane2 dstA = lands_in_c0(L, l) ? x.coeff(0) : x.scratch();
+            int done = 0;
+            TRY(done = w_swt2_fwd_level(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
+                                        l + 1, x.batch, x.s));
+            if (!done) return PDWT_ERR_ARG;   // cannot happen: swt_all_levels_fused() said yes
+            cur = dstA;
+        }
+        return PDWT_OK;
+    }
     Plane2 t1 = x.scratch(), t2 = x.scratch((size_t)Nr * Nc);
-    for (int l = 0; l < x.w.nlevels; l++) {
+    for (int l = 0; l < L; l++) {
         TRY(g_swt_fwd_rows(x.t, l ? x.coeff(0) : x.image(), t1, t2, Nr, Nc, l + 1, x.batch, x.s));
         TRY(g_swt_fwd_cols(x.t, t1, t2, x.coeff(0), x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
                            l + 1, x.batch, x.s));
@@ -418,9 +439,23 @@ int fwd_swt_2d(const Ctx& x)
 
 int inv_swt_2d(const Ctx& x)
 {
-    const int Nr = x.w.Nr, Nc = x.w.Nc;
+    const int Nr = x.w.Nr, Nc = x.w.Nc, L = x.w.nlevels;
+    if (swt_all_levels_fused(x)) {
+        Plane2 cur = x.coeff(0);
+        bool cur_is_c0 = true;
+        for (int l = L - 1; l >= 0; l--) {
+            Plane2 dst = (l == 0) ? x.image() : (cur_is_c0 ? x.scratch() : x.coeff(0));
+            int done = 0;
+            TRY(done = w_swt2_inv_level(x.t, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), dst, Nr, Nc,
+                                        l + 1, x.batch, x.s));
+            if (!done) return PDWT_ERR_ARG;
+            cur = dst;
+            cur_is_c0 = !cur_is_c0;
+        }
+        return PDWT_OK;
+    }
     Plane2 t1 = x.scratch(), t2 = x.scratch((size_t)Nr * Nc);
-    for (int l = x.w.nlevels - 1; l >= 0; l--) {
+    for (int l = L - 1; l >= 0; l--) {
         TRY(g_swt_inv_cols(x.t, x.coeff(0), x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), t1, t2, Nr, Nc,
                            l + 1, x.batch, x.s));
         TRY(g_swt_inv_rows(x.t, t1, t2, l ? x.coeff(0) : x.image(), Nr, Nc, l + 1, x.batch, x.s));

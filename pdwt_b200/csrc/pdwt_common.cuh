@@ -148,6 +148,14 @@ int s_dwt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Pl
 int s_dwt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
                      int batch, cudaStream_t s);
 
+// ---- fused SWT level kernels, pdwt_swt.cu: same convention; w_swt2_supported tells whether EVERY level 1..nlevels of a
+// transform can take them (the caller's buffer plan depends on it)
+int w_swt2_supported(const Taps& t, int Nr, int Nc, int nlevels, int batch);
+int w_swt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int level,
+                     int batch, cudaStream_t s);
+int w_swt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int Nr, int Nc, int level,
+                     int batch, cudaStream_t s);
+
 // ---- element-wise + reductions, pdwt_elementwise.cu ----------------------------------------------------------
 constexpr int kMaxSeg = 64;
 struct SegTable {  // list of (sub-band, length, parameter) handled by one launch

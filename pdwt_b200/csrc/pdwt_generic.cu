@@ -254,6 +254,68 @@ __global__ void __launch_bounds__(GX* GY)
     img[pz * s_img + (size_t)gy * Nc2 + gx] = 0.5f * ((gx & 1) ? __fsub_rn(u, w) : __fadd_rn(u, w));
 }
 
+// Vectorised Haar level for even sizes with nc % 4 == 0 and 16-byte aligned planes: a thread turns 2 x 8 pixels into 4
+// outputs of each sub-band (forward) or back (inverse) -- 128-bit loads and stores only, same expressions and
+// association as above (haar.cu:27-35, 45-54).  Pure streaming: 8 B per pixel and level.
+__device__ __forceinline__ void haar_bfly(float a, float b, float c, float d, float& A, float& V, float& H, float& D)
+{
+    const float sac = __fadd_rn(a, c), sbd = __fadd_rn(b, d), dac = __fsub_rn(a, c), dbd = __fsub_rn(b, d);
+    A = 0.5f * __fadd_rn(sac, sbd);
+    V = 0.5f * __fsub_rn(sac, sbd);
+    H = 0.5f * __fadd_rn(dac, dbd);
+    D = 0.5f * __fsub_rn(dac, dbd);
+}
+__global__ void __launch_bounds__(256)
+    k_haar2d_fwd_v4(const float* __restrict__ img, size_t s_img, float* __restrict__ A, size_t s_a, float* __restrict__ H,
+                    float* __restrict__ V, float* __restrict__ D, size_t s_d, int nr, int nc)
+{
+    const int q = blockIdx.x * 256 + threadIdx.x, gy = blockIdx.y;   // q: group of 4 output columns
+    const size_t pz = blockIdx.z;
+    pdl_wait();
+    if (4 * q >= nc) return;
+    const float4* r0 = reinterpret_cast<const float4*>(img + pz * s_img + (size_t)(2 * gy) * (2 * nc)) + 2 * q;
+    const float4* r1 = r0 + nc / 2;
+    const float4 t0 = __ldg(r0), t1 = __ldg(r0 + 1), b0 = __ldg(r1), b1 = __ldg(r1 + 1);
+    pdl_launch_dependents();
+    float4 oa, ov, oh, od;
+    haar_bfly(t0.x, t0.y, b0.x, b0.y, oa.x, ov.x, oh.x, od.x);
+    haar_bfly(t0.z, t0.w, b0.z, b0.w, oa.y, ov.y, oh.y, od.y);
+    haar_bfly(t1.x, t1.y, b1.x, b1.y, oa.z, ov.z, oh.z, od.z);
+    haar_bfly(t1.z, t1.w, b1.z, b1.w, oa.w, ov.w, oh.w, od.w);
+    const size_t o = (size_t)gy * nc + 4 * q;
+    *reinterpret_cast<float4*>(A + pz * s_a + o) = oa;
+    *reinterpret_cast<float4*>(V + pz * s_d + o) = ov;
+    *reinterpret_cast<float4*>(H + pz * s_d + o) = oh;
+    *reinterpret_cast<float4*>(D + pz * s_d + o) = od;
+}
+// inverse: (a,b,c,d) = (A,V,H,D); out[2y][2x] = .5((a+c)+(b+d)), [2y][2x+1] = .5((a+c)-(b+d)), [2y+1][2x] = .5((a-c)+(b-d)),
+// [2y+1][2x+1] = .5((a-c)-(b-d))  (haar.cu:45-54)
+__global__ void __launch_bounds__(256)
+    k_haar2d_inv_v4(float* __restrict__ img, size_t s_img, const float* __restrict__ A, size_t s_a,
+                    const float* __restrict__ H, const float* __restrict__ V, const float* __restrict__ D, size_t s_d,
+                    int nr, int nc)
+{
+    const int q = blockIdx.x * 256 + threadIdx.x, gy = blockIdx.y;
+    const size_t pz = blockIdx.z;
+    pdl_wait();
+    if (4 * q >= nc) return;
+    const size_t i = (size_t)gy * nc + 4 * q;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(A + pz * s_a + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(V + pz * s_d + i));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(H + pz * s_d + i));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(D + pz * s_d + i));
+    pdl_launch_dependents();
+    float4 t0, t1, b0, b1;
+    // the butterfly is its own inverse pattern: (ee, eo, oe, oo) of one 2x2 block come out in the slots (A, V, H, D)
+    haar_bfly(a.x, b.x, c.x, d.x, t0.x, t0.y, b0.x, b0.y);
+    haar_bfly(a.y, b.y, c.y, d.y, t0.z, t0.w, b0.z, b0.w);
+    haar_bfly(a.z, b.z, c.z, d.z, t1.x, t1.y, b1.x, b1.y);
+    haar_bfly(a.w, b.w, c.w, d.w, t1.z, t1.w, b1.z, b1.w);
+    float4* r0 = reinterpret_cast<float4*>(img + pz * s_img + (size_t)(2 * gy) * (2 * nc)) + 2 * q;
+    float4* r1 = r0 + nc / 2;
+    r0[0] = t0; r0[1] = t1; r1[0] = b0; r1[1] = b1;
+}
+
 // kern_haar1d_fwd, haar.cu:132-146: the factor is a DOUBLE literal (haar.cu:128): float add, double multiply.
 __global__ void __launch_bounds__(GX* GY)
     k_haar1d_fwd(const float* __restrict__ img, size_t s_img, float* __restrict__ A, size_t s_a, float* __restrict__ D,
@@ -482,6 +544,14 @@ int g_swt_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int 
 int g_haar2d_fwd(Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch, cudaStream_t s)
 {
     PDWT_PROF(__func__, s);
+    const int nr = Nr / 2, nc = Nc / 2;
+    if (!(Nr & 1) && !(Nc & 1) && !(nc & 3) && nr <= 65535 && !(img.stride & 3) && !(A.stride & 3) && !(H.stride & 3) &&
+        !(((uintptr_t)img.p | (uintptr_t)A.p | (uintptr_t)H.p | (uintptr_t)V.p | (uintptr_t)D.p) & 15)) {
+        PDWT_CUDA(launch_pdl(k_haar2d_fwd_v4, dim3(idiv_up(nc / 4, 256), nr, batch), 256, 0, s, (const float*)img.p,
+                             img.stride, A.p, A.stride, H.p, V.p, D.p, H.stride, nr, nc));
+        PDWT_LAUNCH_CHECK();
+        return 0;
+    }
     k_haar2d_fwd<<<grid2(half_up(Nc), half_up(Nr), batch), kBlock, 0, s>>>(img.p, img.stride, A.p, A.stride, H.p, V.p,
                                                                           D.p, H.stride, Nr, Nc);
     PDWT_LAUNCH_CHECK();
@@ -491,7 +561,15 @@ int g_haar2d_inv(Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int
                  cudaStream_t s)
 {
     PDWT_PROF(__func__, s);
-    (void)Nr;
+    // Nr x Nc = coefficient plane, Nr2 x Nc2 = output plane
+    if (Nr2 == 2 * Nr && Nc2 == 2 * Nc && !(Nc & 3) && Nr <= 65535 && !(img.stride & 3) && !(A.stride & 3) &&
+        !(H.stride & 3) && !(((uintptr_t)img.p | (uintptr_t)A.p | (uintptr_t)H.p | (uintptr_t)V.p | (uintptr_t)D.p) & 15)) {
+        PDWT_CUDA(launch_pdl(k_haar2d_inv_v4, dim3(idiv_up(Nc / 4, 256), Nr, batch), 256, 0, s, img.p, img.stride,
+                             (const float*)A.p, A.stride, (const float*)H.p, (const float*)V.p, (const float*)D.p,
+                             H.stride, Nr, Nc));
+        PDWT_LAUNCH_CHECK();
+        return 0;
+    }
     k_haar2d_inv<<<grid2(Nc2, Nr2, batch), kBlock, 0, s>>>(img.p, img.stride, A.p, A.stride, H.p, V.p, D.p, H.stride,
                                                           Nc, Nr2, Nc2);
     PDWT_LAUNCH_CHECK();

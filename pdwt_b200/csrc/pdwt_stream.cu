@@ -550,8 +550,9 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
             const long long ctas = (long long)p.ncg * idiv_up(nr, th) * batch;
             const long long full = ctas / ((long long)sms * per_sm), rest = ctas % ((long long)sms * per_sm);
             const double units = (double)(full * per_sm + (rest + sms - 1) / sms) * (th + G::H2 - 1);
-            // prefer at least two CTAs per SM when it is nearly free: a lone warp per scheduler hides no latency
-            const double cost = units * (ctas <= sms ? 1.15 : 1.0);
+            // one CTA per SM = a lone warp per scheduler: measured ~650 cycles per row pair against ~435 per scheduler
+            // with two or more warps sharing it
+            const double cost = units * (ctas <= sms ? 1.5 : 1.0);
             if (cost < best * 0.999) {
                 best = cost;
                 TH = th;

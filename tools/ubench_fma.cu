@@ -25,6 +25,10 @@ __device__ __forceinline__ void fma2(unsigned long long& acc, unsigned long long
 // V3: scalar FFMA with three register operands
 // V4: V2 plus one LDS.128 per 7 FFMA2 (smem co-issue)
 // V5: V0 plus one LDS.128 per 14 FFMA
+// V6: V2 with one ALU instruction (XOR) per FFMA2 -- does an FFMA2 hold the scheduler's issue port for two cycles?
+// V7: scalar FFMA (constant-bank multiplier) with one XOR per TWO FFMA: the same FMA and XOR counts as V6
+// V8: V2 with one XOR per TWO FFMA2 (the ratio of the DWT kernels: ~112 FFMA2 to ~100 other instructions is 1:1,
+//     V6; with the bookkeeping halved it would be V8)
 template <int V, int NCH>
 __global__ void __launch_bounds__(256) kern(const __grid_constant__ Taps t, float* out, int iters, long long* cyc)
 {
@@ -41,6 +45,9 @@ __global__ void __launch_bounds__(256) kern(const __grid_constant__ Taps t, floa
         acc2[i] = 0ull;
     }
     float4 ld = make_float4(0, 0, 0, 0);
+    unsigned z[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) z[i] = threadIdx.x + i;
     long long c0 = clock64();
     for (int it = 0; it < iters; it++) {
 #pragma unroll
@@ -62,6 +69,19 @@ __global__ void __launch_bounds__(256) kern(const __grid_constant__ Taps t, floa
                     float4 q = sm[(threadIdx.x + it + j) & 1023];
                     ld.x += q.x; ld.y += q.y; ld.z += q.z; ld.w += q.w;
                 }
+            } else if (V == 6 || V == 8) {
+#pragma unroll
+                for (int i = 0; i < NCH; i++) {
+                    fma2(acc2[i], pk(x[i], x[i]), pk(t.k[j], t.k[j + 16]));
+                    if (V == 6 || (i & 1)) asm volatile("add.s32 %0, %0, %1;" : "+r"(z[i]) : "r"(z[(i + 3) % NCH]));
+                }
+            } else if (V == 7) {
+#pragma unroll
+                for (int i = 0; i < NCH; i++) {
+                    a[i] = fmaf(x[i], t.k[j], a[i]);
+                    b[i] = fmaf(x[i], t.k[j + 16], b[i]);
+                    asm volatile("add.s32 %0, %0, %1;" : "+r"(z[i]) : "r"(z[(i + 3) % NCH]));
+                }
             } else if (V == 3) {
 #pragma unroll
                 for (int i = 0; i < NCH; i++) a[i] = fmaf(x[i], b[i], a[i]);
@@ -73,7 +93,7 @@ __global__ void __launch_bounds__(256) kern(const __grid_constant__ Taps t, floa
 #pragma unroll
     for (int i = 0; i < NCH; i++) {
         float2 f = *reinterpret_cast<float2*>(&acc2[i]);
-        s += a[i] + f.x + f.y;
+        s += a[i] + f.x + f.y + (float)z[i] + ((V == 7) ? b[i] : 0.f);
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cyc[blockIdx.x] = c1 - c0;
@@ -104,7 +124,7 @@ void run(const char* name, int ctas_per_sm, int threads)
     double mean = 0;
     for (int i = 0; i < grid; i++) mean += h[i];
     mean /= grid;
-    const double fma_per_thread = (double)iters * 14 * NCH * ((V == 1 || V == 2 || V == 4) ? 2 : 1);
+    const double fma_per_thread = (double)iters * 14 * NCH * ((V == 1 || V == 2 || V == 4 || V == 6 || V == 7 || V == 8) ? 2 : 1);
     const double per_sm = fma_per_thread * threads * ctas_per_sm;
     printf("%-34s ctas/sm=%d thr=%d chains=%d : %7.1f FMA/clk/SM   %6.2f TFMA/s  (%.3f ms, %.0f cyc)  err=%s\n", name,
            ctas_per_sm, threads, NCH, per_sm / mean, per_sm * nsm / (ms * 1e-3) / 1e12, ms, mean,
@@ -128,5 +148,12 @@ int main()
     run<2, 8>("FFMA2 x.F32 * (kl,kh)", 1, 128);
     run<4, 8>("FFMA2 + LDS.128 per 7", 2, 256);
     run<5, 8>("FFMA + LDS.128 per 14", 2, 256);
+    run<6, 8>("FFMA2 + XOR 1:1", 2, 256);
+    run<6, 8>("FFMA2 + XOR 1:1", 1, 128);
+    run<6, 8>("FFMA2 + XOR 1:1", 1, 256);
+    run<8, 8>("FFMA2 + XOR 2:1", 2, 256);
+    run<8, 8>("FFMA2 + XOR 2:1", 1, 128);
+    run<7, 8>("2 FFMA + XOR (same work as 1:1)", 2, 256);
+    run<7, 8>("2 FFMA + XOR (same work as 1:1)", 1, 128);
     return 0;
 }
