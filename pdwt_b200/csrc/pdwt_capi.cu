@@ -484,9 +484,15 @@ int fwd_single(const Ctx& x, Family fam)
                 TRY(g_haar1d_fwd(cur, dstA, x.coeff(l + 1), x.w.Nr, Nc, x.batch, x.s));
                 Nc = half_up(Nc);
                 break;
-            case NONSEP:
-                TRY(g_nonsep_fwd(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
-                                 x.batch, x.s));
+            case NONSEP: {
+                int done = 0;
+                if (path_cap() >= 1)
+                    TRY(done = n_nonsep_fwd_level(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2),
+                                                  x.coeff(3 * l + 3), Nr, Nc, x.batch, x.s));
+                if (!done)
+                    TRY(g_nonsep_fwd(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
+                                     x.batch, x.s));
+            }
                 Nr = half_up(Nr);
                 Nc = half_up(Nc);
                 break;
@@ -516,10 +522,16 @@ int inv_single(const Ctx& x, Family fam)
             case HAAR1:
                 TRY(g_haar1d_inv(dst, cur, x.coeff(l + 1), x.w.Nr, half_up(Mc), Mc, x.batch, x.s));
                 break;
-            case NONSEP:
-                TRY(g_nonsep_inv(x.t, dst, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), half_up(Mr),
-                                 half_up(Mc), Mr, Mc, x.batch, x.s));
+            case NONSEP: {
+                int done = 0;
+                if (path_cap() >= 1)
+                    TRY(done = n_nonsep_inv_level(x.t, dst, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2),
+                                                  x.coeff(3 * l + 3), half_up(Mr), half_up(Mc), Mr, Mc, x.batch, x.s));
+                if (!done)
+                    TRY(g_nonsep_inv(x.t, dst, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3),
+                                     half_up(Mr), half_up(Mc), Mr, Mc, x.batch, x.s));
                 break;
+            }
             case NONSEP_SWT:
                 TRY(g_nonsep_swt_inv(x.t, dst, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), x.w.Nr,
                                      x.w.Nc, l + 1, x.batch, x.s));

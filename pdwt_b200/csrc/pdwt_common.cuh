@@ -156,6 +156,12 @@ int w_swt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Pl
 int w_swt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int Nr, int Nc, int level,
                      int batch, cudaStream_t s);
 
+// ---- register-tiled non-separable DWT level kernels, pdwt_nonsep.cu: same convention
+int n_nonsep_fwd_level(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+                       cudaStream_t s);
+int n_nonsep_inv_level(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int Nr2, int Nc2,
+                       int batch, cudaStream_t s);
+
 // ---- element-wise + reductions, pdwt_elementwise.cu ----------------------------------------------------------
 constexpr int kMaxSeg = 64;
 struct SegTable {  // list of (sub-band, length, parameter) handled by one launch

@@ -1,0 +1,326 @@
+// pdwt_nonsep.cu -- tiled kernels of the NON-separable 2-D DWT for sm_100a (BASELINE config C4).
+//
+// The reference gives every output pixel to one thread that walks its hlen x hlen taps through global memory and four
+// constant-memory filters (nonseparable.cu:114-225): 4*hlen^2 FMAs per output with one load per FMA quartet and no
+// reuse.  The transform is FP32-bound (980 flop/pixel for db7, 2 levels), so the kernels here are register-tiled direct
+// convolutions out of shared memory:
+//
+//   forward : a thread owns 4 consecutive output columns x 4 filters.  Per tap row it pulls its 2*3+hlen input samples
+//             with 128-bit shared loads, per tap it reads the four filter values as ONE broadcast 128-bit load and
+//             issues 8 FFMA2:  (A,H)[u] += x.F32 * (K_LL, K_LH),  (V,D)[u] += x.F32 * (K_HL, K_HH).
+//   inverse : the four sub-band tiles are staged interleaved as (A,H) and (V,D) pairs; a thread owns 2 coefficient
+//             positions = a 2 x 4 pixel block.  Per window position it loads the two pairs once and feeds every output
+//             parity whose tap lands there:  (ra,rh) += (a,h) * (K_LL', K_LH'),  (rv,rd) += (v,d) * (K_HL', K_HH').
+//
+// The 2-D filters are the reference's: outer products of the 1-D banks ROUNDED to fp32 (w_outer, nonseparable.cu:16-24,
+// 71-74; note the reference's H/V swap w.r.t. separable mode, SURVEY B2, which comes with them), formed once per CTA in
+// shared memory with __fmul_rn.  Every output is the reference's chain: from 0, taps in (jy, jx) lexicographic order, one
+// fmaf each (fma.rn.f32x2 = two IEEE fmaf); the inverse adds ((ra + rh) + rv) + rd (nonseparable.cu:222-223).
+// Any plane size (the periodic / odd-size folds of nonseparable.cu:139-152 and 205-214 are applied while staging).
+#include "pdwt_common.cuh"
+
+namespace pdwt {
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 ns_pack2(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void ns_unpack2(u64 v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 ns_ffma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ int ns_clamp(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+
+constexpr int kNsThreads = 256;
+
+// ================================================================================================== forward
+template <int HLEN>
+struct NsFwdCfg {
+    static constexpr int U = 4;                      // output columns per thread
+    static constexpr int TW = 64, TH = 16;           // output tile: 16 thread columns x 16 rows
+    static constexpr int C = HLEN / 2 - 1;           // analysis centre, even hlen (nonseparable.cu:121-130)
+    static constexpr int INR = 2 * TH + HLEN - 2;
+    static constexpr int INW = 2 * TW + HLEN - 2;
+    static constexpr int NV = (2 * (U - 1) + HLEN + 3) / 4;   // 16-byte vectors a thread reads per tap row
+    static constexpr int PITCH = ((2 * (TW - U) + 4 * NV + 3) / 4) * 4 + 4;   // floats; >= INW, multiple of 4
+    static constexpr size_t SMEM = sizeof(float) * ((size_t)INR * PITCH + 4 * HLEN * HLEN);
+    static_assert(PITCH >= INW, "tile pitch");
+};
+
+template <int HLEN>
+__global__ void __launch_bounds__(kNsThreads, 2)
+    k_nonsep_fwd_tiled(const __grid_constant__ Taps t, const float* __restrict__ img, size_t s_img, float* __restrict__ A,
+                       size_t s_a, float* __restrict__ H, float* __restrict__ V, float* __restrict__ D, size_t s_d, int Nr,
+                       int Nc)
+{
+    using K = NsFwdCfg<HLEN>;
+    extern __shared__ __align__(16) float smem[];
+    float* S_in = smem;
+    float4* S_k = reinterpret_cast<float4*>(smem + K::INR * K::PITCH);   // [jy][jx] -> (LL, LH, HL, HH)
+    const int tid = threadIdx.x;
+    const int nr = half_up(Nr), nc = half_up(Nc);
+    const int gx0 = blockIdx.x * K::TW, gy0 = blockIdx.y * K::TH;
+    img += (size_t)blockIdx.z * s_img;
+
+    // the four 2-D filters in accumulation order: tap (jy, jx) multiplies K[hlen-1-jy][hlen-1-jx] (nonseparable.cu:155-160)
+    for (int i = tid; i < HLEN * HLEN; i += kNsThreads) {
+        const int jy = i / HLEN, jx = i - jy * HLEN;
+        const float ly = t.L[HLEN - 1 - jy], hy = t.H[HLEN - 1 - jy], lx = t.L[HLEN - 1 - jx], hx = t.H[HLEN - 1 - jx];
+        S_k[i] = make_float4(__fmul_rn(ly, lx), __fmul_rn(ly, hx), __fmul_rn(hy, lx), __fmul_rn(hy, hx));
+    }
+    pdl_wait();
+    // input tile with the reference's fold (periodic; odd sizes repeat the last sample), nonseparable.cu:139-152
+    for (int i = tid; i < K::INR * K::PITCH; i += kNsThreads) {
+        const int r = i / K::PITCH, u = i - r * K::PITCH;
+        const int y = ns_clamp(fold_dec(2 * gy0 - K::C + r, Nr), Nr - 1);
+        const int x = ns_clamp(fold_dec(2 * gx0 - K::C + u, Nc), Nc - 1);
+        S_in[i] = __ldg(img + (size_t)y * Nc + x);
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+
+    const int tx = tid % (K::TW / K::U), ty = tid / (K::TW / K::U);
+    u64 aAH[K::U], aVD[K::U];
+#pragma unroll
+    for (int u = 0; u < K::U; u++) aAH[u] = aVD[u] = 0ull;
+    const float* win = S_in + (2 * ty) * K::PITCH + 2 * K::U * tx;
+#pragma unroll 1
+    for (int jy = 0; jy < HLEN; jy++) {
+        float x[K::NV * 4];
+        const float4* rp = reinterpret_cast<const float4*>(win + jy * K::PITCH);
+#pragma unroll
+        for (int i = 0; i < K::NV; i++) {
+            const float4 f = rp[i];
+            x[4 * i] = f.x; x[4 * i + 1] = f.y; x[4 * i + 2] = f.z; x[4 * i + 3] = f.w;
+        }
+        const float4* kp = S_k + jy * HLEN;
+#pragma unroll
+        for (int jx = 0; jx < HLEN; jx++) {
+            const float4 k = kp[jx];
+            const u64 kah = ns_pack2(k.x, k.y), kvd = ns_pack2(k.z, k.w);
+#pragma unroll
+            for (int u = 0; u < K::U; u++) {
+                const float v = x[2 * u + jx];
+                aAH[u] = ns_ffma2(ns_pack2(v, v), kah, aAH[u]);
+                aVD[u] = ns_ffma2(ns_pack2(v, v), kvd, aVD[u]);
+            }
+        }
+    }
+    const int gy = gy0 + ty, gx = gx0 + K::U * tx;
+    if (gy >= nr || gx >= nc) return;
+    float oa[K::U], oh[K::U], ov[K::U], od[K::U];
+#pragma unroll
+    for (int u = 0; u < K::U; u++) {
+        ns_unpack2(aAH[u], oa[u], oh[u]);
+        ns_unpack2(aVD[u], ov[u], od[u]);
+    }
+    const size_t off = (size_t)gy * nc + gx;
+    float* pa = A + (size_t)blockIdx.z * s_a + off;
+    float* ph = H + (size_t)blockIdx.z * s_d + off;
+    float* pv = V + (size_t)blockIdx.z * s_d + off;
+    float* pd = D + (size_t)blockIdx.z * s_d + off;
+    const bool vec = ((nc & 3) == 0) && ((s_a & 3) == 0) && ((s_d & 3) == 0) &&
+                     (((uintptr_t)A | (uintptr_t)H | (uintptr_t)V | (uintptr_t)D) & 15) == 0;
+    if (vec) {   // nc % 4 == 0 and gx % 4 == 0: the whole vector is inside
+        *reinterpret_cast<float4*>(pa) = make_float4(oa[0], oa[1], oa[2], oa[3]);
+        *reinterpret_cast<float4*>(ph) = make_float4(oh[0], oh[1], oh[2], oh[3]);
+        *reinterpret_cast<float4*>(pv) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        *reinterpret_cast<float4*>(pd) = make_float4(od[0], od[1], od[2], od[3]);
+    } else {
+#pragma unroll
+        for (int u = 0; u < K::U; u++)
+            if (gx + u < nc) {
+                pa[u] = oa[u]; ph[u] = oh[u]; pv[u] = ov[u]; pd[u] = od[u];
+            }
+    }
+}
+
+// ================================================================================================== inverse
+template <int HLEN>
+struct NsInvCfg {
+    static constexpr int H2 = HLEN / 2;
+    static constexpr int CC = H2 / 2;                 // synthesis centre (nonseparable.cu:182-196)
+    static constexpr int SHIFT = (H2 & 1) ? 0 : 1;    // the reference's "virtual id" shift for even hlen/2
+    static constexpr int WIN = H2 + SHIFT;            // coefficient window behind one 2x2 output block, per axis
+    static constexpr int P = 2;                       // coefficient positions (along x) per thread
+    static constexpr int TWC = 64, THC = 8;           // coefficient tile: 32 thread columns x 8 rows
+    static constexpr int INR = THC + WIN - 1;
+    static constexpr int INW = TWC + WIN - 1;
+    static constexpr int PITCH = INW + 1;             // in float2 pairs
+    // (A,H) tile + (V,D) tile as float2, then K'[ey][ex][jy][jx] as float4
+    static constexpr size_t SMEM = sizeof(float2) * 2 * (size_t)INR * PITCH + sizeof(float4) * 4 * H2 * H2;
+};
+
+template <int HLEN>
+__global__ void __launch_bounds__(kNsThreads, 2)
+    k_nonsep_inv_tiled(const __grid_constant__ Taps t, float* __restrict__ img, size_t s_img, const float* __restrict__ A,
+                       size_t s_a, const float* __restrict__ H, const float* __restrict__ V, const float* __restrict__ D,
+                       size_t s_d, int Nr, int Nc, int Nr2, int Nc2)   // Nr x Nc coefficients -> Nr2 x Nc2 pixels
+{
+    using K = NsInvCfg<HLEN>;
+    constexpr int H2 = K::H2, SHIFT = K::SHIFT, WIN = K::WIN;
+    extern __shared__ __align__(16) float smem[];
+    float2* S_ah = reinterpret_cast<float2*>(smem);
+    float2* S_vd = S_ah + K::INR * K::PITCH;
+    float4* S_k = reinterpret_cast<float4*>(S_vd + K::INR * K::PITCH);   // [ey][ex][jy][jx] -> (LL', LH', HL', HH')
+    const int tid = threadIdx.x;
+    const int cx0 = blockIdx.x * K::TWC, cy0 = blockIdx.y * K::THC;
+
+    // synthesis products per output parity e (0 = even output index): tap j multiplies I?[hlen-1-(2j+off_e)] with
+    // off_e = e ? SHIFT : 1-SHIFT (nonseparable.cu:186-204)
+    for (int i = tid; i < 4 * H2 * H2; i += kNsThreads) {
+        const int jx = i % H2, jy = (i / H2) % H2, ex = (i / (H2 * H2)) & 1, ey = i / (2 * H2 * H2);
+        const int oy = ey ? SHIFT : 1 - SHIFT, ox = ex ? SHIFT : 1 - SHIFT;
+        const float ly = t.IL[HLEN - 1 - (2 * jy + oy)], hy = t.IH[HLEN - 1 - (2 * jy + oy)];
+        const float lx = t.IL[HLEN - 1 - (2 * jx + ox)], hx = t.IH[HLEN - 1 - (2 * jx + ox)];
+        S_k[i] = make_float4(__fmul_rn(ly, lx), __fmul_rn(ly, hx), __fmul_rn(hy, lx), __fmul_rn(hy, hx));
+    }
+    pdl_wait();
+    const float* pa = A + (size_t)blockIdx.z * s_a;
+    const float* ph = H + (size_t)blockIdx.z * s_d;
+    const float* pv = V + (size_t)blockIdx.z * s_d;
+    const float* pd = D + (size_t)blockIdx.z * s_d;
+    // coefficient tiles with the reference's single periodic wrap (nonseparable.cu:205-214), interleaved in pairs
+    for (int i = tid; i < K::INR * K::INW; i += kNsThreads) {
+        const int r = i / K::INW, u = i - r * K::INW;
+        int y = cy0 - K::CC + r, x = cx0 - K::CC + u;
+        y += (y < 0) ? Nr : 0;
+        y -= (y >= Nr) ? Nr : 0;
+        x += (x < 0) ? Nc : 0;
+        x -= (x >= Nc) ? Nc : 0;
+        const size_t o = (size_t)ns_clamp(y, Nr - 1) * Nc + ns_clamp(x, Nc - 1);
+        S_ah[r * K::PITCH + u] = make_float2(__ldg(pa + o), __ldg(ph + o));
+        S_vd[r * K::PITCH + u] = make_float2(__ldg(pv + o), __ldg(pd + o));
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+
+    const int tx = tid % (K::TWC / K::P), ty = tid / (K::TWC / K::P);
+    u64 rah[K::P][2][2], rvd[K::P][2][2];   // [position][ey][ex] -> (ra, rh), (rv, rd)
+#pragma unroll
+    for (int p = 0; p < K::P; p++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) rah[p][e >> 1][e & 1] = rvd[p][e >> 1][e & 1] = 0ull;
+    const float2* wah = S_ah + ty * K::PITCH + K::P * tx;
+    const float2* wvd = S_vd + ty * K::PITCH + K::P * tx;
+#pragma unroll 1
+    for (int dy = 0; dy < WIN; dy++) {
+#pragma unroll
+        for (int dx = 0; dx < WIN + K::P - 1; dx++) {   // window column dx of position 0 = column dx-1 of position 1
+            const float2 ah = wah[dy * K::PITCH + dx], vd = wvd[dy * K::PITCH + dx];
+            const u64 dah = ns_pack2(ah.x, ah.y), dvd = ns_pack2(vd.x, vd.y);
+#pragma unroll
+            for (int ey = 0; ey < 2; ey++) {
+                const int jy = dy - (ey ? SHIFT : 0);   // run-time (dy is), uniform
+                if (jy < 0 || jy >= H2) continue;
+#pragma unroll
+                for (int p = 0; p < K::P; p++)
+#pragma unroll
+                    for (int ex = 0; ex < 2; ex++) {
+                        const int jx = dx - p - (ex ? SHIFT : 0);
+                        if (jx < 0 || jx >= H2) continue;   // compile-time
+                        const float4 k = S_k[((ey * 2 + ex) * H2 + jy) * H2 + jx];
+                        rah[p][ey][ex] = ns_ffma2(dah, ns_pack2(k.x, k.y), rah[p][ey][ex]);
+                        rvd[p][ey][ex] = ns_ffma2(dvd, ns_pack2(k.z, k.w), rvd[p][ey][ex]);
+                    }
+            }
+        }
+    }
+    img += (size_t)blockIdx.z * s_img;
+#pragma unroll
+    for (int ey = 0; ey < 2; ey++) {
+        const int gy = 2 * (cy0 + ty) + ey;
+        if (gy >= Nr2) continue;
+#pragma unroll
+        for (int p = 0; p < K::P; p++)
+#pragma unroll
+            for (int ex = 0; ex < 2; ex++) {
+                const int gx = 2 * (cx0 + K::P * tx + p) + ex;
+                if (gx >= Nc2) continue;
+                float ra, rh, rv, rd;
+                ns_unpack2(rah[p][ey][ex], ra, rh);
+                ns_unpack2(rvd[p][ey][ex], rv, rd);
+                img[(size_t)gy * Nc2 + gx] = __fadd_rn(__fadd_rn(__fadd_rn(ra, rh), rv), rd);
+            }
+    }
+}
+
+// ================================================================================================ launchers
+template <int HLEN>
+static int launch_ns_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+                         cudaStream_t s)
+{
+    using K = NsFwdCfg<HLEN>;
+    static bool configured = false;
+    if (!configured) {
+        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+        configured = true;
+    }
+    dim3 grid(idiv_up(half_up(Nc), K::TW), idiv_up(half_up(Nr), K::TH), batch);
+    if (grid.y > 65535u) return 0;
+    PDWT_PROF(prof_tag("k_nonsep_fwd_tiled", Nr, Nc), s);
+    PDWT_CUDA(launch_pdl(k_nonsep_fwd_tiled<HLEN>, grid, kNsThreads, K::SMEM, s, t, (const float*)img.p, img.stride, A.p,
+                         A.stride, H.p, V.p, D.p, H.stride, Nr, Nc));
+    PDWT_LAUNCH_CHECK();
+    return 1;
+}
+
+template <int HLEN>
+static int launch_ns_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int Nr2, int Nc2,
+                         int batch, cudaStream_t s)
+{
+    using K = NsInvCfg<HLEN>;
+    if (Nr < K::WIN || Nc < K::WIN) return 0;   // the single wrap must suffice
+    static bool configured = false;
+    if (!configured) {
+        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_inv_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+        configured = true;
+    }
+    dim3 grid(idiv_up(Nc, K::TWC), idiv_up(Nr, K::THC), batch);
+    if (grid.y > 65535u) return 0;
+    PDWT_PROF(prof_tag("k_nonsep_inv_tiled", Nr2, Nc2), s);
+    PDWT_CUDA(launch_pdl(k_nonsep_inv_tiled<HLEN>, grid, kNsThreads, K::SMEM, s, t, img.p, img.stride, (const float*)A.p,
+                         A.stride, (const float*)H.p, (const float*)V.p, (const float*)D.p, H.stride, Nr, Nc, Nr2, Nc2));
+    PDWT_LAUNCH_CHECK();
+    return 1;
+}
+
+#define PDWT_NS_HLEN_SWITCH(fn, ...)                \
+    switch (t.hlen) {                               \
+        case 4: return fn<4>(__VA_ARGS__);          \
+        case 6: return fn<6>(__VA_ARGS__);          \
+        case 8: return fn<8>(__VA_ARGS__);          \
+        case 10: return fn<10>(__VA_ARGS__);        \
+        case 12: return fn<12>(__VA_ARGS__);        \
+        case 14: return fn<14>(__VA_ARGS__);        \
+        case 16: return fn<16>(__VA_ARGS__);        \
+        case 18: return fn<18>(__VA_ARGS__);        \
+        case 20: return fn<20>(__VA_ARGS__);        \
+        default: return 0;                          \
+    }
+
+// 1 = handled, 0 = shape / filter length not covered (the caller uses the generic kernel), < 0 = error
+int n_nonsep_fwd_level(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
+                       cudaStream_t s)
+{
+    if (batch > 65535 || Nr < t.hlen || Nc < t.hlen) return 0;
+    PDWT_NS_HLEN_SWITCH(launch_ns_fwd, t, img, A, H, V, D, Nr, Nc, batch, s)
+}
+
+int n_nonsep_inv_level(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int Nr2, int Nc2,
+                       int batch, cudaStream_t s)
+{
+    if (batch > 65535) return 0;
+    PDWT_NS_HLEN_SWITCH(launch_ns_inv, t, img, A, H, V, D, Nr, Nc, Nr2, Nc2, batch, s)
+}
+
+}  // namespace pdwt

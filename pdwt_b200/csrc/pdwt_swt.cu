@@ -25,6 +25,14 @@ namespace pdwt {
 constexpr int kSwtThreads = 256;
 constexpr size_t kSwtSmemCap = 200 * 1024;
 
+// 4-byte asynchronous copy global -> shared: the whole tile is in flight at once, no register staging
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all0() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ int wrap1(int i, int N)   // fold_swt as a function of the unwrapped index, then clamped
 {
     i += (i < 0) ? N : 0;
@@ -64,8 +72,9 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
     for (int r = warp; r < K::R; r += kSwtThreads / 32) {
         const int gy = wrap1(ry + f * (mt * K::TH + r - K::C), Nr);
         const float* row = src + (size_t)gy * Nc;
-        for (int u = lane; u < pitch; u += 32) S_in[r * pitch + u] = __ldg(row + wrap1(gx0 - K::C * f + u, Nc));
+        for (int u = lane; u < pitch; u += 32) cp_async4(S_in + r * pitch + u, row + wrap1(gx0 - K::C * f + u, Nc));
     }
+    cp_async_wait_all0();
     __syncthreads();
 
     // ---- row pass, w_kern_forward_swt_pass1 (separable.cu:409-448): lo/hi[x] = sum_j in[x + (j - C) f] * L/H[hlen-1-j]
@@ -164,10 +173,11 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
             const size_t rowo = (size_t)wrap1(ry + f * (mt * K::TH + r - K::C), Nr) * Nc;
             for (int u = lane; u < ci; u += 32) {
                 const size_t o = rowo + wrap1(gx0 - K::C * f + u, Nc);
-                S_c0[r * ci + u] = __ldg(c0 + o);
-                S_c1[r * ci + u] = __ldg(c1 + o);
+                cp_async4(S_c0 + r * ci + u, c0 + o);
+                cp_async4(S_c1 + r * ci + u, c1 + o);
             }
         }
+        cp_async_wait_all0();
         __syncthreads();
         // column pass, w_kern_inverse_swt_pass1 (separable.cu:553-589): t = IL_y(c0) + IH_y(c1), RPT rows per task
         float* S_out = S_t + pair * K::TH * ci;
