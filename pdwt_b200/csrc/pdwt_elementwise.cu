@@ -28,17 +28,28 @@ __global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTa
     size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;
     if (head > n) head = n;
     const size_t nvec = (n - head) >> 2;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    // the grid is sized for the largest segment: a smaller one uses only as many blocks as give a thread >= 4 vectors
+    const size_t nb = min((size_t)gridDim.x, (nvec + 1023) / 1024 + 1);
+    if (blockIdx.x >= nb) return;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = nb * blockDim.x;
     float4* pv = reinterpret_cast<float4*>(p + head);
-    for (size_t i = tid; i < nvec; i += nth) {
-        float4 v = pv[i];
+    auto apply = [&](float4 v) {
         if (HARD) {
             v.x = hard1(v.x, beta); v.y = hard1(v.y, beta); v.z = hard1(v.z, beta); v.w = hard1(v.w, beta);
         } else {
             v.x = soft1(v.x, beta); v.y = soft1(v.y, beta); v.z = soft1(v.z, beta); v.w = soft1(v.w, beta);
         }
-        pv[i] = v;
+        return v;
+    };
+    size_t i = tid;
+    for (; i + 3 * nth < nvec; i += 4 * nth) {   // four independent 128-bit loads in flight per thread
+        const float4 a = pv[i], b = pv[i + nth], c = pv[i + 2 * nth], d = pv[i + 3 * nth];
+        pv[i] = apply(a);
+        pv[i + nth] = apply(b);
+        pv[i + 2 * nth] = apply(c);
+        pv[i + 3 * nth] = apply(d);
     }
+    for (; i < nvec; i += nth) pv[i] = apply(pv[i]);
     if (tid < head) p[tid] = HARD ? hard1(p[tid], beta) : soft1(p[tid], beta);
     const size_t tail0 = head + (nvec << 2);
     if (tail0 + tid < n) p[tail0 + tid] = HARD ? hard1(p[tail0 + tid], beta) : soft1(p[tail0 + tid], beta);
@@ -55,15 +66,20 @@ __global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ SegTable
     size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;
     if (head > n) head = n;
     const size_t nvec = (n - head) >> 2;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    const size_t nb = min((size_t)gridDim.x, (nvec + 1023) / 1024 + 1);   // blocks that take part in this segment
+    if (blockIdx.x >= nb) return;                                        // (no atomic from the others)
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = nb * blockDim.x;
     const float4* pv = reinterpret_cast<const float4*>(p + head);
     double acc = 0.0;
     auto term = [](float v) -> float { return MODE ? v * v : fabsf(v); };
-    for (size_t i = tid; i < nvec; i += nth) {
-        const float4 v = __ldg(pv + i);
-        // the four terms of one vector are added in float (exact enough: 4 terms), the running sum in double
-        acc += (double)((term(v.x) + term(v.y)) + (term(v.z) + term(v.w)));
+    // the four terms of one vector are added in float (exact enough: 4 terms), the running sum in double
+    auto vsum = [&](const float4 v) -> double { return (double)((term(v.x) + term(v.y)) + (term(v.z) + term(v.w))); };
+    size_t i = tid;
+    for (; i + 3 * nth < nvec; i += 4 * nth) {   // four independent 128-bit loads in flight per thread
+        const float4 a = __ldg(pv + i), b = __ldg(pv + i + nth), c = __ldg(pv + i + 2 * nth), d = __ldg(pv + i + 3 * nth);
+        acc += (vsum(a) + vsum(b)) + (vsum(c) + vsum(d));
     }
+    for (; i < nvec; i += nth) acc += vsum(__ldg(pv + i));
     if (tid < head) acc += (double)term(p[tid]);
     const size_t tail0 = head + (nvec << 2);
     if (tail0 + tid < n) acc += (double)term(p[tail0 + tid]);
@@ -82,14 +98,15 @@ __global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ SegTable
     }
 }
 
-static int blocks_for(const SegTable& tab)
+static int blocks_for(const SegTable& tab, int per_sm = 4)
 {
     unsigned long long nmax = 0;
     for (int i = 0; i < tab.nseg; i++) nmax = tab.n[i] > nmax ? tab.n[i] : nmax;
-    // 256 threads x 4 floats x 4 vectors in flight per thread per pass; cap at 8 waves of 148 SMs
+    // 256 threads x 4 floats x 4 vectors in flight per thread per pass; at most 4 blocks per SM per segment (the segment
+    // table puts nseg of these grids side by side)
     unsigned long long b = (nmax + 4095) / 4096;
     if (b < 1) b = 1;
-    if (b > 148 * 8) b = 148 * 8;
+    if (b > 148ull * per_sm) b = 148ull * per_sm;
     return (int)b;
 }
 
@@ -110,7 +127,7 @@ int e_reduce(const SegTable& tab, int mode, int batch, double* d_sums, cudaStrea
 {
     PDWT_PROF(__func__, s);
     if (tab.nseg == 0) return 0;
-    dim3 grid(blocks_for(tab), tab.nseg, batch);
+    dim3 grid(blocks_for(tab, 2), tab.nseg, batch);   // one double atomic per block: keep them few
     if (mode)
         k_reduce<1><<<grid, 256, 0, s>>>(tab, d_sums);
     else

@@ -1,13 +1,19 @@
 #!/bin/bash
-# one gpurun call: parity tests, smoke, micro-benchmark, both bench arms, ncu launch list (+ optional full capture)
-mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-nproc >> gpurun_out/smi.txt
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
-[ -x tools/bin/ubench_fma ] && tools/bin/ubench_fma > gpurun_out/ubench_fma.txt 2>&1
-python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-python bench.py --steps 40 --warmup 5 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
-tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -2; cat gpurun_out/ubench_fma.txt; cat gpurun_out/bench_ref.json; cat gpurun_out/bench_ours.json; tail -3 gpurun_out/bench_ours.err
+# one gpurun call that produces everything profiles/ holds for a round: parity tests, smoke, both bench arms, the batched
+# workloads, the ncu launch list of the bench command and one ncu --set full capture of the six level kernels
+TAG=${1:-r01g}
+O=gpurun_out/$TAG; mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader > $O/smi.txt 2>&1; nproc >> $O/smi.txt
+( time python -m pytest tests -m gpu -x -q ) > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" >> $O/smoke.log
+python bench.py --impl reference --steps 20 --warmup 3 > $O/bench_ref.json 2> $O/bench_ref.err
+python bench.py --steps 40 --warmup 5 > $O/bench_ours.json 2> $O/bench_ours.err
+python bench.py --steps 10 --warmup 3 --workload c5 --no-cpu > $O/bench_c5_n1.json 2> $O/bench_c5.err
+python bench.py --steps 10 --warmup 3 --workload c2b8 --no-cpu > $O/bench_c2b8.json 2> $O/bench_c2b8.err
+python tools/bench_configs.py > $O/configs.jsonl 2> $O/configs.err
+python tools/prof_seq.py > $O/sequence.txt 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu > $O/bench_under_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_ -s 12 -c 6 -o $O/ncu_c2 python tools/prof_fwdinv.py 3 > $O/ncu_c2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_ -s 6 -c 6 -o $O/ncu_b16 python tools/prof_batch.py > $O/ncu_b16.log 2>&1
+tail -3 $O/pytest_gpu.log; tail -2 $O/smoke.log; cut -c1-300 $O/bench_ref.json; cut -c1-300 $O/bench_ours.json; cat $O/sequence.txt | head -5
