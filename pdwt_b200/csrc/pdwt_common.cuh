@@ -156,6 +156,13 @@ int w_swt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Pl
 int w_swt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int Nr, int Nc, int level,
                      int batch, cudaStream_t s);
 
+// ---- staged row-pass kernels of the (batched) 1-D transforms, pdwt_rows.cu: same convention; the g_*_rows launchers try
+// them first
+int r_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int Nc, int batch, cudaStream_t s);
+int r_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int n, int M, int batch, cudaStream_t s);
+int r_swt_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int Nc, int level, int batch, cudaStream_t s);
+int r_swt_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int Nc, int level, int batch, cudaStream_t s);
+
 // ---- register-tiled non-separable DWT level kernels, pdwt_nonsep.cu: same convention
 int n_nonsep_fwd_level(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
                        cudaStream_t s);

@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(GX* GY)
 // ---------------------------------------------------------------------------------------------------- launchers
 int g_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int Nc, int batch, cudaStream_t s)
 {
+    if (const int d = r_fwd_rows(t, img, lo, hi, Nr, Nc, batch, s)) return d < 0 ? d : 0;   // staged row kernels
     PDWT_PROF(__func__, s);
     k_fwd_rows<<<grid2(half_up(Nc), Nr, batch), kBlock, 0, s>>>(t, img.p, img.stride, lo.p, lo.stride, hi.p, hi.stride,
                                                                 Nr, Nc);
@@ -500,6 +501,7 @@ int g_inv_cols(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 t1,
 }
 int g_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int n, int M, int batch, cudaStream_t s)
 {
+    if (const int d = r_inv_rows(t, t1, t2, img, Nr, n, M, batch, s)) return d < 0 ? d : 0;
     PDWT_PROF(__func__, s);
     k_inv_rows<<<grid2(M, Nr, batch), kBlock, 0, s>>>(t, t1.p, t1.stride, t2.p, t2.stride, img.p, img.stride, Nr, n, M);
     PDWT_LAUNCH_CHECK();
@@ -508,6 +510,7 @@ int g_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int n, i
 int g_swt_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int Nc, int level, int batch,
                    cudaStream_t s)
 {
+    if (const int d = r_swt_fwd_rows(t, img, lo, hi, Nr, Nc, level, batch, s)) return d < 0 ? d : 0;
     PDWT_PROF(__func__, s);
     k_swt_fwd_rows<<<grid2(Nc, Nr, batch), kBlock, 0, s>>>(t, img.p, img.stride, lo.p, lo.stride, hi.p, hi.stride, Nr,
                                                            Nc, 1 << (level - 1));
@@ -535,6 +538,7 @@ int g_swt_inv_cols(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2
 int g_swt_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int Nc, int level, int batch,
                    cudaStream_t s)
 {
+    if (const int d = r_swt_inv_rows(t, t1, t2, img, Nr, Nc, level, batch, s)) return d < 0 ? d : 0;
     PDWT_PROF(__func__, s);
     k_swt_inv_rows<<<grid2(Nc, Nr, batch), kBlock, 0, s>>>(t, t1.p, t1.stride, t2.p, t2.stride, img.p, img.stride, Nr,
                                                            Nc, 1 << (level - 1));

@@ -37,10 +37,10 @@ def timeit(fn, iters, warm=3):
     return (time.perf_counter() - t0) / iters * 1e6
 
 
-def run(tag, shape, wname, levels, sep, swt, seq, iters, bytes_per_px):
+def run(tag, shape, wname, levels, sep, swt, seq, iters, bytes_per_px, ndim=2):
     x = rnd(shape, 0)
     out = {"config": tag, "shape": list(shape), "wavelet": wname, "levels": levels, "iters": iters}
-    W = pdwt_b200.Wavelets(torch.from_numpy(x).cuda(), wname, levels, do_separable=sep, do_swt=swt)
+    W = pdwt_b200.Wavelets(torch.from_numpy(x).cuda(), wname, levels, do_separable=sep, do_swt=swt, ndim=ndim)
     L = pdwt_b200.lib()
     l0 = L.pdwt_launch_count()
     us = timeit(lambda: seq(W, None), iters)
@@ -48,7 +48,7 @@ def run(tag, shape, wname, levels, sep, swt, seq, iters, bytes_per_px):
     out["ours_launches_per_iter"] = (L.pdwt_launch_count() - l0) // (iters + 3)
     out["ours_alg_GBs"] = round(bytes_per_px * x.size / us / 1e3, 1)
     if R is not None:
-        h = R.ref_create(x.ctypes.data_as(fp), shape[0], shape[1], wname.encode(), levels, 1, sep, 0, swt, 2)
+        h = R.ref_create(x.ctypes.data_as(fp), shape[0], shape[1], wname.encode(), levels, 1, sep, 0, swt, ndim)
         us_r = timeit(lambda: seq(None, h), iters)
         out["ref_us"] = round(us_r, 1)
         out["speedup"] = round(us_r / us, 2)
@@ -71,7 +71,7 @@ def seq_c4(W, h):   # README.md:90-103 -- forward, norm1, soft_threshold, norm1,
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c3", "c4", "c4db2", "haar", "c2seq"]
+    which = sys.argv[1:] or ["c3", "c4", "c4db2", "haar", "c2seq", "dwt1d", "swt1d", "haar1d", "nsswt", "odd"]
     if "c3" in which:
         run("C3 swt sym8 L4 2048^2 fwd+inv", (2048, 2048), "sym8", 4, 1, 1, seq_fwd_inv, 10, 112)
     if "c4" in which:
@@ -82,3 +82,13 @@ if __name__ == "__main__":
         run("haar L3 4096^2 fwd+inv", (4096, 4096), "haar", 3, 1, 0, seq_fwd_inv, 20, 16)
     if "c2seq" in which:
         run("separable db7 L3 4096^2 fwd,norm1,soft,norm1,inv", (4096, 4096), "db7", 3, 1, 0, seq_c4, 20, 31.5)
+    if "dwt1d" in which:
+        run("1-D DWT db7 L3, 4096 rows of 4096 fwd+inv", (4096, 4096), "db7", 3, 1, 0, seq_fwd_inv, 20, 16, ndim=1)
+    if "swt1d" in which:
+        run("1-D SWT db4 L3, 4096 rows of 4096 fwd+inv", (4096, 4096), "db4", 3, 1, 1, seq_fwd_inv, 10, 64, ndim=1)
+    if "haar1d" in which:
+        run("1-D haar L3, 4096 rows of 4096 fwd+inv", (4096, 4096), "haar", 3, 1, 0, seq_fwd_inv, 20, 16, ndim=1)
+    if "nsswt" in which:
+        run("non-separable SWT db2 L2 1024^2 fwd+inv", (1024, 1024), "db2", 2, 0, 1, seq_fwd_inv, 10, 64)
+    if "odd" in which:
+        run("separable db7 L3 4095x4097 (odd sizes) fwd+inv", (4095, 4097), "db7", 3, 1, 0, seq_fwd_inv, 20, 16)
