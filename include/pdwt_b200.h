@@ -121,6 +121,17 @@ int pdwt_call_soft_thresh(float** d_coeffs, float beta, pdwt_w_info winfos, int 
                           int batch, void* stream);
 int pdwt_call_hard_thresh(float** d_coeffs, float beta, pdwt_w_info winfos, int do_thresh_appcoeffs, int normalize,
                           int batch, void* stream);
+/* the other proximal operators and coefficient helpers of the class */
+int pdwt_call_group_soft_thresh(float** d_coeffs, float beta, pdwt_w_info winfos, int do_thresh_appcoeffs, int normalize,
+                                int batch, void* stream);                       /* w_call_group_soft_thresh common.cu:311 */
+int pdwt_call_proj_linf(float** d_coeffs, float beta, pdwt_w_info winfos, int do_thresh_appcoeffs, int batch,
+                        void* stream);                                          /* w_call_proj_linf         common.cu:285 */
+int pdwt_shrink(float** d_coeffs, float beta, pdwt_w_info winfos, int do_thresh_appcoeffs, int batch,
+                void* stream);                                                  /* w_shrink                 common.cu:343 */
+int pdwt_add_coeffs(float** dst, float** src, pdwt_w_info winfos, float alpha, int batch,
+                    void* stream);                                              /* w_add_coeffs(_1d)        common.cu:499 */
+int pdwt_call_circshift(float* d_image, float* d_image2, pdwt_w_info winfos, int sr, int sc, int inplace, int batch,
+                        void* stream);                                          /* w_call_circshift         common.cu:375 */
 
 /* Wavelets::norm1 / ::norm2sq, wt.cu:398-418 / 370-395 (cuBLAS asum / nrm2 replaced by one warp-shuffle
  * reduction kernel over all sub-bands).  out: HOST array of `batch` floats, one norm per plane; synchronises
@@ -145,7 +156,8 @@ typedef struct pdwt_wavelets pdwt_wavelets;
 /* Wavelets::Wavelets(img, Nr, Nc, wname, levels, memisonhost, do_separable, do_cycle_spinning, do_swt, ndim),
  * wt.cu:84-185.  img may be NULL (zero image).  Always returns an object unless allocation fails; creation
  * problems are reported the reference's way through state == PDWT_W_CREATION_ERROR (an unknown wavelet sets it
- * instead of hanging).  do_cycle_spinning != 0 is refused (out of scope). */
+ * instead of hanging).  do_cycle_spinning: forward() applies a random circular shift (rand(), as the
+ * reference, wt.cu:242-246) and inverse() undoes it. */
 int pdwt_wavelets_create(pdwt_wavelets** out, const float* img, int Nr, int Nc, const char* wname, int levels,
                          int memisonhost, int do_separable, int do_cycle_spinning, int do_swt, int ndim, int batch);
 int pdwt_wavelets_copy(pdwt_wavelets** out, const pdwt_wavelets* src); /* copy-ctor, wt.cu:191-222 */
@@ -155,6 +167,12 @@ int pdwt_wavelets_forward(pdwt_wavelets* w);                       /* wt.cu:236-
 int pdwt_wavelets_inverse(pdwt_wavelets* w);                       /* wt.cu:273-307 */
 int pdwt_wavelets_soft_threshold(pdwt_wavelets* w, float beta, int do_thresh_appcoeffs, int normalize); /* :310 */
 int pdwt_wavelets_hard_threshold(pdwt_wavelets* w, float beta, int do_thresh_appcoeffs, int normalize); /* :320 */
+int pdwt_wavelets_group_soft_threshold(pdwt_wavelets* w, float beta, int do_thresh_appcoeffs, int normalize); /* wt.cu:330 */
+int pdwt_wavelets_shrink(pdwt_wavelets* w, float beta, int do_thresh_appcoeffs);     /* wt.cu:341 */
+int pdwt_wavelets_proj_linf(pdwt_wavelets* w, float beta, int do_thresh_appcoeffs);  /* wt.cu:350 */
+int pdwt_wavelets_circshift(pdwt_wavelets* w, int sr, int sc, int inplace);          /* wt.cu:365 */
+int pdwt_wavelets_add_wavelet(pdwt_wavelets* w, const pdwt_wavelets* other, float alpha); /* wt.cu:624; the reference's codes */
+int pdwt_wavelets_current_shift(const pdwt_wavelets* w, int* sr, int* sc);            /* current_shift_r / _c, wt.h:27-28 */
 int pdwt_wavelets_norm1(pdwt_wavelets* w, float* out);             /* wt.cu:398; out[batch] on the host */
 int pdwt_wavelets_norm2sq(pdwt_wavelets* w, float* out);           /* wt.cu:370 */
 int pdwt_wavelets_get_image(pdwt_wavelets* w, float* img);         /* wt.cu:421; returns the element count */

@@ -58,6 +58,10 @@ class Wavelets {
     void forward();
     void soft_threshold(DTYPE beta, int do_thresh_appcoeffs = 0, int normalize = 0);
     void hard_threshold(DTYPE beta, int do_thresh_appcoeffs = 0, int normalize = 0);
+    void group_soft_threshold(DTYPE beta, int do_thresh_appcoeffs = 0, int normalize = 0);
+    void shrink(DTYPE beta, int do_thresh_appcoeffs = 1);
+    void proj_linf(DTYPE beta, int do_thresh_appcoeffs = 1);
+    void circshift(int sr, int sc, int inplace = 1);
     void inverse();
     DTYPE norm2sq();
     DTYPE norm1();
@@ -69,6 +73,8 @@ class Wavelets {
     int set_filters_forward(char* filtername, unsigned int len, DTYPE* filter1, DTYPE* filter2, DTYPE* filter3 = 0,
                             DTYPE* filter4 = 0);
     int set_filters_inverse(DTYPE* filter1, DTYPE* filter2, DTYPE* filter3 = 0, DTYPE* filter4 = 0);
+    int add_wavelet(Wavelets W, DTYPE alpha = 1.0f);              // by value, like the reference (wt.h:73)
+    int add_wavelet_ref(const Wavelets& W, DTYPE alpha = 1.0f);   // the same without the deep copy
     __intptr_t image_int_ptr(void);
     __intptr_t coeff_int_ptr(int num);
 

@@ -60,6 +60,16 @@ def lib() -> C.CDLL:
         L.orc_filters_custom.argtypes = [C.POINTER(OrcFilters), C.c_int, _fp, _fp, _fp, _fp]
         L.orc_threshold.argtypes = [_fpp, C.c_float, OrcInfo, C.c_int, C.c_int, C.c_int]
         L.orc_threshold.restype = None
+        L.orc_proj_linf.argtypes = [_fpp, C.c_float, OrcInfo, C.c_int]
+        L.orc_proj_linf.restype = None
+        L.orc_shrink.argtypes = [_fpp, C.c_float, OrcInfo, C.c_int]
+        L.orc_shrink.restype = None
+        L.orc_group_soft_thresh.argtypes = [_fpp, C.c_float, OrcInfo, C.c_int, C.c_int, C.c_int]
+        L.orc_group_soft_thresh.restype = None
+        L.orc_add_coeffs.argtypes = [_fpp, _fpp, OrcInfo, C.c_float]
+        L.orc_add_coeffs.restype = None
+        L.orc_circshift.argtypes = [_fp, _fp, OrcInfo, C.c_int, C.c_int]
+        L.orc_circshift.restype = None
         L.orc_norm1.argtypes = [_fpp, OrcInfo]
         L.orc_norm1.restype = C.c_float
         L.orc_norm2sq.argtypes = [_fpp, OrcInfo, C.c_int]
@@ -174,6 +184,43 @@ class Wavelets:
         if self.state == W_INVERSE:
             return
         self.L.orc_threshold(self._cptr, float(beta), self.info, int(do_thresh_appcoeffs), int(normalize), 1)
+
+    # ---- the other proximal operators and helpers, wt.cu:330-368, 624-657 ----------------------------------
+    def group_soft_threshold(self, beta, do_thresh_appcoeffs=0, normalize=0, variant=0):
+        if self.state == W_INVERSE:
+            return
+        self.L.orc_group_soft_thresh(self._cptr, float(beta), self.info, int(do_thresh_appcoeffs), int(normalize),
+                                     int(variant))
+
+    def shrink(self, beta, do_thresh_appcoeffs=1):
+        if self.state == W_INVERSE:
+            return
+        self.L.orc_shrink(self._cptr, float(beta), self.info, int(do_thresh_appcoeffs))
+
+    def proj_linf(self, beta, do_thresh_appcoeffs=1):
+        if self.state == W_INVERSE:
+            return
+        self.L.orc_proj_linf(self._cptr, float(beta), self.info, int(do_thresh_appcoeffs))
+
+    def circshift(self, sr, sc, inplace=1):
+        out = np.empty_like(self.image)
+        self.L.orc_circshift(_ptr(self.image), _ptr(out), self.info, int(sr), int(sc))
+        if inplace:
+            self.image[...] = out
+        else:
+            self.tmp[: out.size] = out.ravel()
+
+    def add_wavelet(self, W, alpha=1.0) -> int:
+        if self.info.nlevels != W.info.nlevels or self.wname.lower() != W.wname.lower():
+            return -1
+        if self.state == W_INVERSE or W.state == W_INVERSE:
+            return 1
+        if (self.info.Nr, self.info.Nc, self.info.ndims) != (W.info.Nr, W.info.Nc, W.info.ndims):
+            return -2
+        if bool(self.info.do_swt) != bool(W.info.do_swt):
+            return -3
+        self.L.orc_add_coeffs(self._cptr, W._cptr, self.info, float(alpha))
+        return 0
 
     def norm1(self) -> float:
         return float(self.L.orc_norm1(self._cptr, self.info))

@@ -25,6 +25,17 @@ void ref_hard_threshold(void* w, float beta, int app, int normalize)
 {
     static_cast<Wavelets*>(w)->hard_threshold(beta, app, normalize);
 }
+void ref_group_soft_threshold(void* w, float beta, int app, int normalize)
+{
+    static_cast<Wavelets*>(w)->group_soft_threshold(beta, app, normalize);
+}
+void ref_shrink(void* w, float beta, int app) { static_cast<Wavelets*>(w)->shrink(beta, app); }
+void ref_proj_linf(void* w, float beta, int app) { static_cast<Wavelets*>(w)->proj_linf(beta, app); }
+void ref_circshift(void* w, int sr, int sc, int inplace) { static_cast<Wavelets*>(w)->circshift(sr, sc, inplace); }
+int ref_add_wavelet(void* w, void* other, float alpha)
+{
+    return static_cast<Wavelets*>(w)->add_wavelet(*static_cast<Wavelets*>(other), alpha);   // by value: deep copy
+}
 float ref_norm1(void* w) { return static_cast<Wavelets*>(w)->norm1(); }
 float ref_norm2sq(void* w) { return static_cast<Wavelets*>(w)->norm2sq(); }
 int ref_get_image(void* w, float* out) { return static_cast<Wavelets*>(w)->get_image(out); }

@@ -99,6 +99,17 @@ def lib() -> C.CDLL:
         getattr(L, n).argtypes = [vp]
     for n in ("pdwt_wavelets_soft_threshold", "pdwt_wavelets_hard_threshold"):
         getattr(L, n).argtypes = [vp, cf, ci, ci]
+    L.pdwt_wavelets_group_soft_threshold.argtypes = [vp, cf, ci, ci]
+    L.pdwt_wavelets_shrink.argtypes = [vp, cf, ci]
+    L.pdwt_wavelets_proj_linf.argtypes = [vp, cf, ci]
+    L.pdwt_wavelets_circshift.argtypes = [vp, ci, ci, ci]
+    L.pdwt_wavelets_add_wavelet.argtypes = [vp, vp, cf]
+    L.pdwt_wavelets_current_shift.argtypes = [vp, C.POINTER(ci), C.POINTER(ci)]
+    L.pdwt_call_group_soft_thresh.argtypes = [C.POINTER(vp), cf, WInfo, ci, ci, ci, vp]
+    for n in ("pdwt_call_proj_linf", "pdwt_shrink"):
+        getattr(L, n).argtypes = [C.POINTER(vp), cf, WInfo, ci, ci, vp]
+    L.pdwt_add_coeffs.argtypes = [C.POINTER(vp), C.POINTER(vp), WInfo, cf, ci, vp]
+    L.pdwt_call_circshift.argtypes = [vp, vp, WInfo, ci, ci, ci, ci, vp]
     for n in ("pdwt_wavelets_norm1", "pdwt_wavelets_norm2sq", "pdwt_wavelets_get_image"):
         getattr(L, n).argtypes = [vp, vp]
     L.pdwt_wavelets_get_coeff.argtypes = [vp, vp, ci]
@@ -205,8 +216,7 @@ class Wavelets:
         self._L = L
         self._keep = None
         self.batch = int(batch)
-        if self.state == W_CREATION_ERROR and L.pdwt_last_cuda_error() and self.info.hlen > 0 and self.info.nlevels > 0 \
-                and not do_cycle_spinning:
+        if self.state == W_CREATION_ERROR and L.pdwt_last_cuda_error() and self.info.hlen > 0 and self.info.nlevels > 0:
             raise PdwtError("Wavelets construction failed on the device: " + L.pdwt_last_cuda_error_string().decode())
 
     # ---- lifetime -------------------------------------------------------------------------------------------
@@ -296,6 +306,35 @@ class Wavelets:
         rc = self._L.pdwt_wavelets_hard_threshold(self._h, float(beta), int(do_thresh_appcoeffs), int(normalize))
         if rc != PDWT_ERR_STATE:
             _check(rc, "hard_threshold")
+
+    def group_soft_threshold(self, beta: float, do_thresh_appcoeffs: int = 0, normalize: int = 0):
+        rc = self._L.pdwt_wavelets_group_soft_threshold(self._h, float(beta), int(do_thresh_appcoeffs), int(normalize))
+        if rc != PDWT_ERR_STATE:
+            _check(rc, "group_soft_threshold")
+
+    def shrink(self, beta: float, do_thresh_appcoeffs: int = 1):
+        rc = self._L.pdwt_wavelets_shrink(self._h, float(beta), int(do_thresh_appcoeffs))
+        if rc != PDWT_ERR_STATE:
+            _check(rc, "shrink")
+
+    def proj_linf(self, beta: float, do_thresh_appcoeffs: int = 1):
+        rc = self._L.pdwt_wavelets_proj_linf(self._h, float(beta), int(do_thresh_appcoeffs))
+        if rc != PDWT_ERR_STATE:
+            _check(rc, "proj_linf")
+
+    def circshift(self, sr: int, sc: int, inplace: int = 1):
+        """circular shift of the image (wt.cu:365); inplace=0 leaves the result in d_tmp like the reference"""
+        _check(self._L.pdwt_wavelets_circshift(self._h, int(sr), int(sc), int(inplace)), "circshift")
+
+    def add_wavelet(self, other: "Wavelets", alpha: float = 1.0) -> int:
+        """coefficients += alpha * other's (wt.cu:624-657); returns the reference's codes (0 ok, 1 / -1..-4 refused)"""
+        return self._L.pdwt_wavelets_add_wavelet(self._h, other._h, float(alpha))
+
+    @property
+    def current_shift(self):
+        r, c = C.c_int(), C.c_int()
+        self._L.pdwt_wavelets_current_shift(self._h, C.byref(r), C.byref(c))
+        return r.value, c.value
 
     def _norm(self, fn):
         out = np.zeros(self.batch, dtype=np.float32)

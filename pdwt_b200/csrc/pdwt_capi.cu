@@ -615,7 +615,8 @@ namespace {
 // segment table of every sub-band in the reference's visiting order: details of level 1..L first, A last
 // (wt.cu:404-417).  beta_of(level) < 0 skips nothing; `with_app` adds A_L (logical size).
 int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with_details, bool with_app,
-                  const float* beta_levels, float beta_app, int op /*0 soft,1 hard,2 asum,3 sumsq*/, double* d_sums,
+                  const float* beta_levels, float beta_app, int op /*0 soft,1 hard,2 asum,3 sumsq,4 proj_linf,5 scale*/,
+                  double* d_sums,
                   int* nseg_out)
 {
     SegTable tab;
@@ -626,8 +627,10 @@ int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with
         int rc;
         if (op < 2)
             rc = e_threshold(tab, op, batch, s);
-        else
+        else if (op < 4)
             rc = e_reduce(tab, op - 2, batch, d_sums, s);
+        else
+            rc = e_threshold(tab, op - 2, batch, s);   // element-wise ops 2 (proj_linf) and 3 (scale)
         tab.nseg = 0;
         return rc;
     };
@@ -635,7 +638,7 @@ int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with
         int r, cdim;
         if (pdwt_coeff_dims(w, k, &r, &cdim) != PDWT_OK) return PDWT_ERR_ARG;
         if (!c[k]) return PDWT_ERR_ARG;
-        if (op >= 2 && tab.nseg == kMaxSeg) return PDWT_ERR_ARG;  // reductions need one table (sums layout)
+        if ((op == 2 || op == 3) && tab.nseg == kMaxSeg) return PDWT_ERR_ARG;  // reductions need one table (sums layout)
         if (tab.nseg == kMaxSeg) TRY(flush());
         tab.ptr[tab.nseg] = c[k];
         tab.n[tab.nseg] = (unsigned long long)r * cdim;
@@ -670,6 +673,42 @@ int threshold_impl(float** c, float beta, pdwt_w_info w, int app, int normalize,
         bl[l] = beta;
     }
     return launch_tables(c, w, batch, s, true, app != 0, bl, beta_app, hard ? 1 : 0, nullptr, nullptr);
+}
+
+// w_call_proj_linf (common.cu:285-308) and w_shrink (common.cu:343-369): one element-wise launch over the sub-bands
+int elementwise_impl(float** c, float beta, pdwt_w_info w, int app, int batch, cudaStream_t s, int op)
+{
+    if (!c || w.nlevels < 1 || w.nlevels > 32 || batch < 1) return PDWT_ERR_ARG;
+    float bl[32];
+    for (int l = 0; l < w.nlevels; l++) bl[l] = beta;
+    return launch_tables(c, w, batch, s, true, app != 0, bl, beta, op, nullptr, nullptr);
+}
+
+// w_call_group_soft_thresh, common.cu:311-341
+int group_soft_impl(float** c, float beta, pdwt_w_info w, int app, int normalize, int batch, cudaStream_t s)
+{
+    if (!c || w.nlevels < 1 || w.nlevels > 32 || batch < 1) return PDWT_ERR_ARG;
+    GroupTable tab;
+    memset(&tab, 0, sizeof tab);
+    tab.nlev = w.nlevels;
+    tab.stride_a = pdwt_coeff_alloc_elems(w, 0);
+    for (int l = 0; l < w.nlevels; l++) {
+        if (normalize > 0) beta = (float)((double)beta / 1.4142135623730951);   // common.cu:335 (SQRT_2 is a double)
+        const int kd = (w.ndims == 2) ? 3 * l + 3 : l + 1;
+        int r, cc;
+        if (pdwt_coeff_dims(w, kd, &r, &cc) != PDWT_OK || !c[kd]) return PDWT_ERR_ARG;
+        if (w.ndims == 2) {
+            if (!c[3 * l + 1] || !c[3 * l + 2]) return PDWT_ERR_ARG;
+            tab.h[l] = c[3 * l + 1];
+            tab.v[l] = c[3 * l + 2];
+        }
+        tab.d[l] = c[kd];
+        tab.a[l] = (app && l == w.nlevels - 1) ? c[0] : nullptr;
+        tab.n[l] = (unsigned long long)r * cc;
+        tab.stride_d[l] = pdwt_coeff_alloc_elems(w, kd);
+        tab.beta[l] = beta;
+    }
+    return e_group_soft(tab, batch, s);
 }
 
 }  // namespace
@@ -715,6 +754,58 @@ int pdwt_call_hard_thresh(float** d_coeffs, float beta, pdwt_w_info winfos, int 
                           int batch, void* stream)
 {
     return threshold_impl(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, (cudaStream_t)stream, 1);
+}
+
+int pdwt_call_group_soft_thresh(float** d_coeffs, float beta, pdwt_w_info winfos, int do_thresh_appcoeffs, int normalize,
+                                int batch, void* stream)
+{
+    return group_soft_impl(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, (cudaStream_t)stream);
+}
+int pdwt_call_proj_linf(float** d_coeffs, float beta, pdwt_w_info winfos, int do_thresh_appcoeffs, int batch, void* stream)
+{
+    return elementwise_impl(d_coeffs, beta, winfos, do_thresh_appcoeffs, batch, (cudaStream_t)stream, 4);
+}
+int pdwt_shrink(float** d_coeffs, float beta, pdwt_w_info winfos, int do_thresh_appcoeffs, int batch, void* stream)
+{
+    return elementwise_impl(d_coeffs, 1.0f / (1.0f + beta), winfos, do_thresh_appcoeffs, batch, (cudaStream_t)stream, 5);
+}
+/* w_add_coeffs / w_add_coeffs_1d, common.cu:499-526: dst += alpha * src for every sub-band (logical sizes; the
+ * reference's 1-D variant halves with floor and so skips the tail of odd-sized levels -- fixed here) */
+int pdwt_add_coeffs(float** dst, float** src, pdwt_w_info w, float alpha, int batch, void* stream)
+{
+    if (!dst || !src || w.nlevels < 1 || batch < 1) return PDWT_ERR_ARG;
+    const int nseg = pdwt_num_coeffs(w);
+    if (nseg > kMaxSeg) return PDWT_ERR_ARG;
+    PairTable tab;
+    memset(&tab, 0, sizeof tab);
+    for (int k = 0; k < nseg; k++) {
+        int r, c;
+        if (pdwt_coeff_dims(w, k, &r, &c) != PDWT_OK || !dst[k] || !src[k]) return PDWT_ERR_ARG;
+        tab.dst[k] = dst[k];
+        tab.src[k] = src[k];
+        tab.n[k] = (unsigned long long)r * c;
+        tab.stride_dst[k] = tab.stride_src[k] = pdwt_coeff_alloc_elems(w, k);
+    }
+    tab.nseg = nseg;
+    return e_axpy(tab, alpha, batch, (cudaStream_t)stream);
+}
+/* w_call_circshift, common.cu:375-395.  inplace: the result is in d_image (d_image2 is scratch), else in d_image2. */
+int pdwt_call_circshift(float* d_image, float* d_image2, pdwt_w_info w, int sr, int sc, int inplace, int batch, void* stream)
+{
+    if (!d_image || !d_image2 || w.Nr < 1 || w.Nc < 1 || batch < 1) return PDWT_ERR_ARG;
+    const int Nr = w.Nr, Nc = w.Nc;
+    if (sr < 0) sr += Nr;
+    if (sc < 0) sc += Nc;
+    sr = ((sr % Nr) + Nr) % Nr;
+    sc = ((sc % Nc) + Nc) % Nc;
+    if (w.ndims == 1) sr = 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t plane = (size_t)Nr * Nc;
+    if (inplace) {
+        PDWT_CUDA(cudaMemcpyAsync(d_image2, d_image, sizeof(float) * plane * batch, cudaMemcpyDeviceToDevice, s));
+        return e_circshift(d_image2, d_image, plane, Nr, Nc, sr, sc, batch, s);
+    }
+    return e_circshift(d_image, d_image2, plane, Nr, Nc, sr, sc, batch, s);
 }
 
 static int norm_entry(float** d_coeffs, pdwt_w_info w, int batch, float* out, void* stream, int mode)

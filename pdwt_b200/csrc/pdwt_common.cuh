@@ -178,7 +178,22 @@ struct SegTable {  // list of (sub-band, length, parameter) handled by one launc
     unsigned long long stride[kMaxSeg];  // floats between planes
     float beta[kMaxSeg];
 };
-int e_threshold(const SegTable& tab, int hard, int batch, cudaStream_t s);
+int e_threshold(const SegTable& tab, int op /*0 soft, 1 hard, 2 proj_linf, 3 scale by beta*/, int batch, cudaStream_t s);
+struct GroupTable {  // group soft threshold: per level the detail triple (h, v NULL in 1-D) and, optionally, A
+    int nlev;
+    float *h[32], *v[32], *d[32], *a[32];
+    unsigned long long n[32], stride_d[32], stride_a;
+    float beta[32];
+};
+int e_group_soft(const GroupTable& tab, int batch, cudaStream_t s);
+struct PairTable {  // dst += alpha * src, sub-band by sub-band
+    int nseg;
+    float* dst[kMaxSeg];
+    const float* src[kMaxSeg];
+    unsigned long long n[kMaxSeg], stride_dst[kMaxSeg], stride_src[kMaxSeg];
+};
+int e_axpy(const PairTable& tab, float alpha, int batch, cudaStream_t s);
+int e_circshift(const float* in, float* out, size_t stride, int Nr, int Nc, int sr, int sc, int batch, cudaStream_t s);
 // sums[plane*nseg + seg] (double, device) += sum |v| (mode 0) or sum v^2 (mode 1)
 int e_reduce(const SegTable& tab, int mode, int batch, double* d_sums, cudaStream_t s);
 

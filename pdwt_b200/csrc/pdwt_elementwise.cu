@@ -17,7 +17,16 @@ __device__ __forceinline__ float hard1(float v, float beta)
     return fmaxf(s, 0.0f) * v;
 }
 
-template <int HARD>
+// w_kern_proj_linf*, common.cu:101-138: projection onto the L-infinity ball
+__device__ __forceinline__ float linf1(float v, float beta) { return copysignf(fminf(fabsf(v), beta), v); }
+// OP: 0 soft, 1 hard, 2 proj_linf, 3 scale by beta (w_shrink's cublas scal, common.cu:343-369)
+template <int OP>
+__device__ __forceinline__ float ew1(float v, float beta)
+{
+    return OP == 0 ? soft1(v, beta) : OP == 1 ? hard1(v, beta) : OP == 2 ? linf1(v, beta) : __fmul_rn(beta, v);
+}
+
+template <int OP>
 __global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTable tab)
 {
     const int seg = blockIdx.y;
@@ -34,11 +43,7 @@ __global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTa
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = nb * blockDim.x;
     float4* pv = reinterpret_cast<float4*>(p + head);
     auto apply = [&](float4 v) {
-        if (HARD) {
-            v.x = hard1(v.x, beta); v.y = hard1(v.y, beta); v.z = hard1(v.z, beta); v.w = hard1(v.w, beta);
-        } else {
-            v.x = soft1(v.x, beta); v.y = soft1(v.y, beta); v.z = soft1(v.z, beta); v.w = soft1(v.w, beta);
-        }
+        v.x = ew1<OP>(v.x, beta); v.y = ew1<OP>(v.y, beta); v.z = ew1<OP>(v.z, beta); v.w = ew1<OP>(v.w, beta);
         return v;
     };
     size_t i = tid;
@@ -50,9 +55,9 @@ __global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTa
         pv[i + 3 * nth] = apply(d);
     }
     for (; i < nvec; i += nth) pv[i] = apply(pv[i]);
-    if (tid < head) p[tid] = HARD ? hard1(p[tid], beta) : soft1(p[tid], beta);
+    if (tid < head) p[tid] = ew1<OP>(p[tid], beta);
     const size_t tail0 = head + (nvec << 2);
-    if (tail0 + tid < n) p[tail0 + tid] = HARD ? hard1(p[tail0 + tid], beta) : soft1(p[tail0 + tid], beta);
+    if (tail0 + tid < n) p[tail0 + tid] = ew1<OP>(p[tail0 + tid], beta);
 }
 
 // sum |v| (MODE 0) or sum v^2 (MODE 1): per-thread double accumulation of float4 loads, warp shuffle tree,
@@ -110,15 +115,114 @@ static int blocks_for(const SegTable& tab, int per_sm = 4)
     return (int)b;
 }
 
-int e_threshold(const SegTable& tab, int hard, int batch, cudaStream_t s)
+int e_threshold(const SegTable& tab, int op, int batch, cudaStream_t s)
 {
     PDWT_PROF(__func__, s);
     if (tab.nseg == 0) return 0;
     dim3 grid(blocks_for(tab), tab.nseg, batch);
-    if (hard)
-        k_threshold<1><<<grid, 256, 0, s>>>(tab);
-    else
-        k_threshold<0><<<grid, 256, 0, s>>>(tab);
+    switch (op) {
+        case 0: k_threshold<0><<<grid, 256, 0, s>>>(tab); break;
+        case 1: k_threshold<1><<<grid, 256, 0, s>>>(tab); break;
+        case 2: k_threshold<2><<<grid, 256, 0, s>>>(tab); break;
+        default: k_threshold<3><<<grid, 256, 0, s>>>(tab); break;
+    }
+    PDWT_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- group soft threshold, w_kern_group_soft_thresh(_1d), common.cu:141-196: one scaling factor per position from the
+// Euclidean norm of (H, V, D[, A]) -- or (D[, A]) in 1-D -- at that position.  The expression is written exactly as in the
+// reference so that nvcc contracts it the same way (the golden vectors pin the result).
+__global__ void __launch_bounds__(256) k_group_soft(const __grid_constant__ GroupTable tab)
+{
+    const int lev = blockIdx.y;
+    const size_t n = tab.n[lev], pz = blockIdx.z;
+    const float beta = tab.beta[lev];
+    float* c_h = tab.h[lev] ? tab.h[lev] + pz * tab.stride_d[lev] : nullptr;
+    float* c_v = tab.v[lev] ? tab.v[lev] + pz * tab.stride_d[lev] : nullptr;
+    float* c_d = tab.d[lev] + pz * tab.stride_d[lev];
+    float* c_a = tab.a[lev] ? tab.a[lev] + pz * tab.stride_a : nullptr;
+    for (size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += (size_t)gridDim.x * blockDim.x) {
+        float val_h = 0.0f, val_v = 0.0f, val_d = 0.0f, val_a = 0.0f;
+        float norm = 0, res = 0;
+        val_d = c_d[tid];
+        if (c_h) {   // 2-D
+            val_h = c_h[tid];
+            val_v = c_v[tid];
+            norm = val_h * val_h + val_v * val_v + val_d * val_d;
+        } else {
+            norm = val_d * val_d;
+        }
+        if (c_a != nullptr) {
+            val_a = c_a[tid];
+            norm += val_a * val_a;
+        }
+        norm = sqrtf(norm);
+        if (norm == 0)
+            res = 0;
+        else
+            res = max(1 - beta / norm, 0.0);
+        if (c_h) {
+            c_h[tid] *= res;
+            c_v[tid] *= res;
+        }
+        c_d[tid] *= res;
+        if (c_a != nullptr) c_a[tid] *= res;
+    }
+}
+
+int e_group_soft(const GroupTable& tab, int batch, cudaStream_t s)
+{
+    PDWT_PROF(__func__, s);
+    if (tab.nlev == 0) return 0;
+    unsigned long long nmax = 0;
+    for (int i = 0; i < tab.nlev; i++) nmax = tab.n[i] > nmax ? tab.n[i] : nmax;
+    unsigned long long b = (nmax + 1023) / 1024;
+    b = b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b);
+    k_group_soft<<<dim3((unsigned)b, tab.nlev, batch), 256, 0, s>>>(tab);
+    PDWT_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- dst += alpha * src over a table of sub-band pairs (w_add_coeffs, common.cu:499-526: cublas axpy)
+__global__ void __launch_bounds__(256) k_axpy(const __grid_constant__ PairTable tab, float alpha)
+{
+    const int seg = blockIdx.y;
+    const size_t n = tab.n[seg], pz = blockIdx.z;
+    float* dst = tab.dst[seg] + pz * tab.stride_dst[seg];
+    const float* src = tab.src[seg] + pz * tab.stride_src[seg];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = fmaf(alpha, src[i], dst[i]);
+}
+int e_axpy(const PairTable& tab, float alpha, int batch, cudaStream_t s)
+{
+    PDWT_PROF(__func__, s);
+    if (tab.nseg == 0) return 0;
+    unsigned long long nmax = 0;
+    for (int i = 0; i < tab.nseg; i++) nmax = tab.n[i] > nmax ? tab.n[i] : nmax;
+    unsigned long long b = (nmax + 1023) / 1024;
+    b = b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b);
+    k_axpy<<<dim3((unsigned)b, tab.nseg, batch), 256, 0, s>>>(tab, alpha);
+    PDWT_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- circular shift, w_kern_circshift (common.cu:200-211): out[y][x] = in[(y - sr) mod Nr][(x - sc) mod Nc]
+__global__ void __launch_bounds__(256) k_circshift(const float* __restrict__ in, float* __restrict__ out, size_t stride,
+                                                   int Nr, int Nc, int sr, int sc)
+{
+    const int gx = blockIdx.x * 256 + threadIdx.x, gy = blockIdx.y;
+    if (gx >= Nc) return;
+    int r = gy - sr, c = gx - sc;
+    if (r < 0) r += Nr;
+    if (c < 0) c += Nc;
+    out[(size_t)blockIdx.z * stride + (size_t)gy * Nc + gx] = in[(size_t)blockIdx.z * stride + (size_t)r * Nc + c];
+}
+int e_circshift(const float* in, float* out, size_t stride, int Nr, int Nc, int sr, int sc, int batch, cudaStream_t s)
+{
+    PDWT_PROF(__func__, s);
+    if (Nr > 65535 || batch > 65535) return PDWT_ERR_ARG;
+    k_circshift<<<dim3(idiv_up(Nc, 256), Nr, batch), 256, 0, s>>>(in, out, stride, Nr, Nc, sr, sc);
     PDWT_LAUNCH_CHECK();
     return 0;
 }

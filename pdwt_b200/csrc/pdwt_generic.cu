@@ -344,6 +344,45 @@ __global__ void __launch_bounds__(GX* GY)
     img[pz * s_img + (size_t)gy * Nc2 + gx] = (float)(0.70710678118654746 * (double)r);
 }
 
+// Vectorised 1-D Haar level for even widths with nc % 4 == 0 and 16-byte aligned planes: 8 samples <-> 4 + 4 coefficients
+// per thread, 128-bit accesses, the reference's float add / double multiply / round sequence (haar.cu:128,143-157).
+__device__ __forceinline__ float haar_s(float v) { return (float)(0.70710678118654746 * (double)v); }
+__global__ void __launch_bounds__(256)
+    k_haar1d_fwd_v4(const float* __restrict__ img, size_t s_img, float* __restrict__ A, size_t s_a, float* __restrict__ D,
+                    size_t s_d, int nc)
+{
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    const size_t row = blockIdx.y, pz = blockIdx.z;
+    pdl_wait();
+    if (4 * q >= nc) return;
+    const float4* r = reinterpret_cast<const float4*>(img + pz * s_img + row * (2 * (size_t)nc)) + 2 * q;
+    const float4 x0 = __ldg(r), x1 = __ldg(r + 1);
+    pdl_launch_dependents();
+    const size_t o = row * nc + 4 * q;
+    *reinterpret_cast<float4*>(A + pz * s_a + o) = make_float4(haar_s(__fadd_rn(x0.x, x0.y)), haar_s(__fadd_rn(x0.z, x0.w)),
+                                                              haar_s(__fadd_rn(x1.x, x1.y)), haar_s(__fadd_rn(x1.z, x1.w)));
+    *reinterpret_cast<float4*>(D + pz * s_d + o) = make_float4(haar_s(__fsub_rn(x0.x, x0.y)), haar_s(__fsub_rn(x0.z, x0.w)),
+                                                              haar_s(__fsub_rn(x1.x, x1.y)), haar_s(__fsub_rn(x1.z, x1.w)));
+}
+__global__ void __launch_bounds__(256)
+    k_haar1d_inv_v4(float* __restrict__ img, size_t s_img, const float* __restrict__ A, size_t s_a,
+                    const float* __restrict__ D, size_t s_d, int nc)
+{
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    const size_t row = blockIdx.y, pz = blockIdx.z;
+    pdl_wait();
+    if (4 * q >= nc) return;
+    const size_t i = row * nc + 4 * q;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(A + pz * s_a + i));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(D + pz * s_d + i));
+    pdl_launch_dependents();
+    float4* r = reinterpret_cast<float4*>(img + pz * s_img + row * (2 * (size_t)nc)) + 2 * q;
+    r[0] = make_float4(haar_s(__fadd_rn(a.x, d.x)), haar_s(__fsub_rn(a.x, d.x)), haar_s(__fadd_rn(a.y, d.y)),
+                       haar_s(__fsub_rn(a.y, d.y)));
+    r[1] = make_float4(haar_s(__fadd_rn(a.z, d.z)), haar_s(__fsub_rn(a.z, d.z)), haar_s(__fadd_rn(a.w, d.w)),
+                       haar_s(__fsub_rn(a.w, d.w)));
+}
+
 // ---------------------------------------------------------------------------------------------- non-separable
 // The four 2-D filters are outer products of the 1-D banks rounded to float on the host (w_outer,
 // nonseparable.cu:16-24,71-74): K_LL[i][j] = L[i]*L[j], K_LH = L[i]*H[j], K_HL = H[i]*L[j], K_HH = H[i]*H[j] with i
@@ -582,6 +621,13 @@ int g_haar2d_inv(Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int
 int g_haar1d_fwd(Plane2 img, Plane2 A, Plane2 D, int Nr, int Nc, int batch, cudaStream_t s)
 {
     PDWT_PROF(__func__, s);
+    if (!(Nc & 7) && Nr <= 65535 && !(img.stride & 3) && !(A.stride & 3) && !(D.stride & 3) &&
+        !(((uintptr_t)img.p | (uintptr_t)A.p | (uintptr_t)D.p) & 15)) {
+        PDWT_CUDA(launch_pdl(k_haar1d_fwd_v4, dim3(idiv_up(Nc / 8, 256), Nr, batch), 256, 0, s, (const float*)img.p,
+                             img.stride, A.p, A.stride, D.p, D.stride, Nc / 2));
+        PDWT_LAUNCH_CHECK();
+        return 0;
+    }
     k_haar1d_fwd<<<grid2(half_up(Nc), Nr, batch), kBlock, 0, s>>>(img.p, img.stride, A.p, A.stride, D.p, D.stride, Nr,
                                                                  Nc);
     PDWT_LAUNCH_CHECK();
@@ -590,6 +636,13 @@ int g_haar1d_fwd(Plane2 img, Plane2 A, Plane2 D, int Nr, int Nc, int batch, cuda
 int g_haar1d_inv(Plane2 img, Plane2 A, Plane2 D, int Nr, int Nc, int Nc2, int batch, cudaStream_t s)
 {
     PDWT_PROF(__func__, s);
+    if (Nc2 == 2 * Nc && !(Nc & 3) && Nr <= 65535 && !(img.stride & 3) && !(A.stride & 3) && !(D.stride & 3) &&
+        !(((uintptr_t)img.p | (uintptr_t)A.p | (uintptr_t)D.p) & 15)) {
+        PDWT_CUDA(launch_pdl(k_haar1d_inv_v4, dim3(idiv_up(Nc / 4, 256), Nr, batch), 256, 0, s, img.p, img.stride,
+                             (const float*)A.p, A.stride, (const float*)D.p, D.stride, Nc));
+        PDWT_LAUNCH_CHECK();
+        return 0;
+    }
     k_haar1d_inv<<<grid2(Nc2, Nr, batch), kBlock, 0, s>>>(img.p, img.stride, A.p, A.stride, D.p, D.stride, Nr, Nc, Nc2);
     PDWT_LAUNCH_CHECK();
     return 0;

@@ -167,11 +167,6 @@ Wavelets::Wavelets(DTYPE* img, int Nr, int Nc, const char* name, int levels, int
     W_TRY(cuda_rc(cudaMalloc(&d_coeffs[0], sizeof(DTYPE) * a_elems)), W_CREATION_ERROR);
     W_TRY(cuda_rc(cudaMemset(d_coeffs[0], 0, sizeof(DTYPE) * a_elems)), W_CREATION_ERROR);
 
-    if (do_cycle_spinning) {  // out of scope: refuse rather than silently ignore
-        puts("ERROR: cycle spinning is not provided by pdwt_b200 (use the SWT for translation invariance).");
-        last_error = PDWT_ERR_ARG;
-        state = W_CREATION_ERROR;
-    }
 }
 
 // Copy constructor (deep), reference wt.cu:191-222
@@ -222,6 +217,12 @@ void Wavelets::forward()
         return;
     }
     const long long before = pdwt_launch_count();
+    if (do_cycle_spinning) {   // wt.cu:242-246: a random circular shift of the image before the transform
+        current_shift_r = rand() % winfos.Nr;
+        current_shift_c = rand() % winfos.Nc;
+        W_TRY(pdwt_call_circshift(d_image, d_tmp, winfos, current_shift_r, current_shift_c, 1, batch, stream),
+              W_FORWARD_ERROR);
+    }
     W_TRY(pdwt_forward(filters, d_image, d_coeffs, d_tmp, winfos, batch, stream, do_separable), W_FORWARD_ERROR);
     launches += pdwt_launch_count() - before;
     state = W_FORWARD;
@@ -240,6 +241,9 @@ void Wavelets::inverse()
     }
     const long long before = pdwt_launch_count();
     W_TRY(pdwt_inverse(filters, d_image, d_coeffs, d_tmp, winfos, batch, stream, do_separable), W_INVERSE_ERROR);
+    if (do_cycle_spinning)     // wt.cu:305: shift back
+        W_TRY(pdwt_call_circshift(d_image, d_tmp, winfos, -current_shift_r, -current_shift_c, 1, batch, stream),
+              W_INVERSE_ERROR);
     launches += pdwt_launch_count() - before;
     state = W_INVERSE;
 }
@@ -270,6 +274,93 @@ void Wavelets::hard_threshold(DTYPE beta, int do_thresh_appcoeffs, int normalize
     W_TRY(pdwt_call_hard_thresh(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, stream),
           W_THRESHOLD_ERROR);
     launches += pdwt_launch_count() - before;
+}
+
+// reference wt.cu:330-338
+void Wavelets::group_soft_threshold(DTYPE beta, int do_thresh_appcoeffs, int normalize)
+{
+    if (state == W_INVERSE) {
+        puts("Warning: Wavelets(): cannot threshold coefficients, as they were modified by W.inverse()");
+        return;
+    }
+    if (state == W_CREATION_ERROR) return;
+    const long long before = pdwt_launch_count();
+    W_TRY(pdwt_call_group_soft_thresh(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, stream),
+          W_THRESHOLD_ERROR);
+    launches += pdwt_launch_count() - before;
+}
+
+// reference wt.cu:341-348 (L2 proximal: every coefficient times 1/(1+beta))
+void Wavelets::shrink(DTYPE beta, int do_thresh_appcoeffs)
+{
+    if (state == W_INVERSE) {
+        puts("Warning: Wavelets(): cannot threshold coefficients, as they were modified by W.inverse()");
+        return;
+    }
+    if (state == W_CREATION_ERROR) return;
+    const long long before = pdwt_launch_count();
+    W_TRY(pdwt_shrink(d_coeffs, beta, winfos, do_thresh_appcoeffs, batch, stream), W_THRESHOLD_ERROR);
+    launches += pdwt_launch_count() - before;
+}
+
+// reference wt.cu:350-358 (projection onto the L-infinity ball)
+void Wavelets::proj_linf(DTYPE beta, int do_thresh_appcoeffs)
+{
+    if (state == W_INVERSE) {
+        puts("Warning: Wavelets(): cannot threshold coefficients, as they were modified by W.inverse()");
+        return;
+    }
+    if (state == W_CREATION_ERROR) return;
+    const long long before = pdwt_launch_count();
+    W_TRY(pdwt_call_proj_linf(d_coeffs, beta, winfos, do_thresh_appcoeffs, batch, stream), W_THRESHOLD_ERROR);
+    launches += pdwt_launch_count() - before;
+}
+
+// reference wt.cu:365-367.  inplace = 1: result in d_image; otherwise in d_tmp.
+void Wavelets::circshift(int sr, int sc, int inplace)
+{
+    if (state == W_CREATION_ERROR || !d_image) return;
+    const long long before = pdwt_launch_count();
+    const int rc = pdwt_call_circshift(d_image, d_tmp, winfos, sr, sc, inplace, batch, stream);
+    if (rc < 0) last_error = rc;
+    launches += pdwt_launch_count() - before;
+}
+
+// reference wt.cu:624-657: this += alpha * W (coefficients only); same checks and return codes
+int Wavelets::add_wavelet(Wavelets W, DTYPE alpha) { return add_wavelet_ref(W, alpha); }
+int Wavelets::add_wavelet_ref(const Wavelets& W, DTYPE alpha)
+{
+    if ((winfos.nlevels != W.winfos.nlevels) || (strcasecmp(wname, W.wname))) {
+        puts("ERROR: add_wavelet(): right operand is not the same transform (wname, level)");
+        return -1;
+    }
+    if (state == W_INVERSE || W.state == W_INVERSE) {
+        puts("WARNING: add_wavelet(): this operation makes no sense when wavelet has just been inverted");
+        return 1;
+    }
+    if (winfos.Nr != W.winfos.Nr || winfos.Nc != W.winfos.Nc || winfos.ndims != W.winfos.ndims || batch != W.batch) {
+        puts("ERROR: add_wavelet(): operands do not have the same geometry");
+        return -2;
+    }
+    if ((winfos.do_swt != 0) ^ (W.winfos.do_swt != 0)) {
+        puts("ERROR: add_wavelet(): operands should both use SWT or DWT");
+        return -3;
+    }
+    if ((do_cycle_spinning * W.do_cycle_spinning) &&
+        ((current_shift_r != W.current_shift_r) || (current_shift_c != W.current_shift_c))) {
+        puts("ERROR: add_wavelet(): operands do not have the same current shift");
+        return -4;
+    }
+    if (!d_coeffs || !W.d_coeffs) return -2;
+    if (W.stream != stream) cudaStreamSynchronize((cudaStream_t)W.stream);   // the operand's pending work
+    const long long before = pdwt_launch_count();
+    const int rc = pdwt_add_coeffs(d_coeffs, W.d_coeffs, winfos, alpha, batch, stream);
+    launches += pdwt_launch_count() - before;
+    if (rc < 0) {
+        last_error = rc;
+        return rc;
+    }
+    return 0;
 }
 
 int Wavelets::norms(int mode, DTYPE* out)
@@ -510,6 +601,46 @@ int pdwt_wavelets_hard_threshold(pdwt_wavelets* w, float beta, int app, int norm
     if (w->W.state == W_INVERSE || w->W.state == W_CREATION_ERROR) return PDWT_ERR_STATE;
     w->W.hard_threshold(beta, app, normalize);
     return after(w, W_THRESHOLD_ERROR);
+}
+int pdwt_wavelets_group_soft_threshold(pdwt_wavelets* w, float beta, int app, int normalize)
+{
+    CHECK_W;
+    if (w->W.state == W_INVERSE || w->W.state == W_CREATION_ERROR) return PDWT_ERR_STATE;
+    w->W.group_soft_threshold(beta, app, normalize);
+    return after(w, W_THRESHOLD_ERROR);
+}
+int pdwt_wavelets_shrink(pdwt_wavelets* w, float beta, int app)
+{
+    CHECK_W;
+    if (w->W.state == W_INVERSE || w->W.state == W_CREATION_ERROR) return PDWT_ERR_STATE;
+    w->W.shrink(beta, app);
+    return after(w, W_THRESHOLD_ERROR);
+}
+int pdwt_wavelets_proj_linf(pdwt_wavelets* w, float beta, int app)
+{
+    CHECK_W;
+    if (w->W.state == W_INVERSE || w->W.state == W_CREATION_ERROR) return PDWT_ERR_STATE;
+    w->W.proj_linf(beta, app);
+    return after(w, W_THRESHOLD_ERROR);
+}
+int pdwt_wavelets_circshift(pdwt_wavelets* w, int sr, int sc, int inplace)
+{
+    CHECK_W;
+    if (w->W.state == W_CREATION_ERROR) return PDWT_ERR_STATE;
+    w->W.circshift(sr, sc, inplace);
+    return PDWT_OK;
+}
+int pdwt_wavelets_add_wavelet(pdwt_wavelets* w, const pdwt_wavelets* other, float alpha)
+{
+    if (!w || !other) return PDWT_ERR_ARG;
+    return w->W.add_wavelet_ref(other->W, alpha);   // no by-value copy across the C boundary
+}
+int pdwt_wavelets_current_shift(const pdwt_wavelets* w, int* sr, int* sc)
+{
+    if (!w) return PDWT_ERR_ARG;
+    if (sr) *sr = w->W.current_shift_r;
+    if (sc) *sc = w->W.current_shift_c;
+    return PDWT_OK;
 }
 int pdwt_wavelets_norm1(pdwt_wavelets* w, float* out) { CHECK_W; return w->W.norm1_batched(out); }
 int pdwt_wavelets_norm2sq(pdwt_wavelets* w, float* out) { CHECK_W; return w->W.norm2sq_batched(out); }
