@@ -15,6 +15,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-fPIC,-O2,-Wall", "-Xptxas", "-v"] + (["-DPDWT_EXPERIMENTS"] if os.environ.get("PDWT_EXPERIMENTS") else [])
 
 
+PER_FILE_FLAGS = {}   # extra nvcc flags for single sources (none at present)
+
+
 def _deps():
     d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     d += [os.path.join(HERE, "..", "include", f) for f in ("pdwt_b200.h", "wt.h")]
@@ -33,7 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = ["nvcc", *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = ["nvcc", *NVCC_FLAGS, *PER_FILE_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

@@ -33,6 +33,37 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* src)
 }
 __device__ __forceinline__ void cp_async_wait_all0() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 sw_pack2(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void sw_unpack2(u64 v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// two IEEE fp32 operations per instruction (FFMA2 / FMUL2 / FADD2): packing changes no bit
+__device__ __forceinline__ u64 sw_ffma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 sw_fmul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 sw_fadd2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 __device__ __forceinline__ int wrap1(int i, int N)   // fold_swt as a function of the unwrapped index, then clamped
 {
     i += (i < 0) ? N : 0;
@@ -50,13 +81,15 @@ struct SwtFwdCfg {
     static size_t smem(int f) { return sizeof(float) * ((size_t)R * (TW + (HLEN - 1) * f) + 2 * (size_t)R * TW); }
 };
 
-template <int HLEN>
+// F = compile-time dilation (tap offsets become immediates), 0 = run-time `f_rt`
+template <int HLEN, int F>
 __global__ void __launch_bounds__(kSwtThreads, 2)
     k_swt_fwd_fused(const __grid_constant__ Taps t, const float* __restrict__ src, size_t s_src, float* __restrict__ A,
                     size_t s_a, float* __restrict__ H, float* __restrict__ V, float* __restrict__ D, size_t s_d, int Nr,
-                    int Nc, int f)
+                    int Nc, int f_rt)
 {
     using K = SwtFwdCfg<HLEN>;
+    const int f = F ? F : f_rt;
     extern __shared__ __align__(16) float smem[];
     const int pitch = K::TW + (HLEN - 1) * f;
     float* S_in = smem;
@@ -82,13 +115,14 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
 #pragma unroll
         for (int xx = lane; xx < K::TW; xx += 32) {
             const float* p = S_in + r * pitch + xx;
-            float lo = 0.f, hi = 0.f;
+            u64 lh = 0ull;   // (lo, hi) += v * (L, H)[hlen-1-j]
 #pragma unroll
             for (int j = 0; j < HLEN; j++) {
                 const float v = p[j * f];
-                lo = fmaf(v, t.L[HLEN - 1 - j], lo);
-                hi = fmaf(v, t.H[HLEN - 1 - j], hi);
+                lh = sw_ffma2(sw_pack2(v, v), sw_pack2(t.L[HLEN - 1 - j], t.H[HLEN - 1 - j]), lh);
             }
+            float lo, hi;
+            sw_unpack2(lh, lo, hi);
             S_lo[r * K::TW + xx] = lo;
             S_hi[r * K::TW + xx] = hi;
         }
@@ -101,21 +135,20 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
     const int xx = tid % K::TW;
     const int gx = gx0 + xx;
     for (int m0 = (tid / K::TW) * K::RPT; m0 < K::TH; m0 += (kSwtThreads / K::TW) * K::RPT) {
-        float a[K::RPT], h[K::RPT], v[K::RPT], d[K::RPT];
+        u64 ah[K::RPT], vd[K::RPT];   // (A, H) += lo * (L, H)[..],  (V, D) += hi * (L, H)[..]
 #pragma unroll
-        for (int o = 0; o < K::RPT; o++) a[o] = h[o] = v[o] = d[o] = 0.f;
+        for (int o = 0; o < K::RPT; o++) ah[o] = vd[o] = 0ull;
 #pragma unroll
         for (int i = 0; i < K::RPT + HLEN - 1; i++) {
             const float v1 = S_lo[(m0 + i) * K::TW + xx], v2 = S_hi[(m0 + i) * K::TW + xx];
+            const u64 p1 = sw_pack2(v1, v1), p2 = sw_pack2(v2, v2);
 #pragma unroll
             for (int o = 0; o < K::RPT; o++) {
                 const int j = i - o;
                 if (j >= 0 && j < HLEN) {
-                    const float kl = t.L[HLEN - 1 - j], kh = t.H[HLEN - 1 - j];
-                    a[o] = fmaf(v1, kl, a[o]);
-                    h[o] = fmaf(v1, kh, h[o]);
-                    v[o] = fmaf(v2, kl, v[o]);
-                    d[o] = fmaf(v2, kh, d[o]);
+                    const u64 k = sw_pack2(t.L[HLEN - 1 - j], t.H[HLEN - 1 - j]);
+                    ah[o] = sw_ffma2(p1, k, ah[o]);
+                    vd[o] = sw_ffma2(p2, k, vd[o]);
                 }
             }
         }
@@ -124,10 +157,13 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
             const int gy = ry + f * (mt * K::TH + m0 + o);
             if (gy < Nr && gx < Nc) {
                 const size_t off = (size_t)gy * Nc + gx;
-                A[(size_t)blockIdx.z * s_a + off] = a[o];
-                H[(size_t)blockIdx.z * s_d + off] = h[o];
-                V[(size_t)blockIdx.z * s_d + off] = v[o];
-                D[(size_t)blockIdx.z * s_d + off] = d[o];
+                float a, h, v, d;
+                sw_unpack2(ah[o], a, h);
+                sw_unpack2(vd[o], v, d);
+                A[(size_t)blockIdx.z * s_a + off] = a;
+                H[(size_t)blockIdx.z * s_d + off] = h;
+                V[(size_t)blockIdx.z * s_d + off] = v;
+                D[(size_t)blockIdx.z * s_d + off] = d;
             }
         }
     }
@@ -144,16 +180,25 @@ struct SwtInvCfg {
     static size_t smem(int f) { return sizeof(float) * (2 * (size_t)R + 2 * (size_t)TH) * (TW + (HLEN - 1) * f); }
 };
 
-// one synthesis tap of the reference: res += v * k / 2  ==  round(v*k), exact halving, add (separable.cu:581-584)
-__device__ __forceinline__ float swt_acc(float res, float v, float k) { return __fadd_rn(res, __fmul_rn(v, k) * 0.5f); }
-
+// One synthesis tap of the reference: res += v * k / 2 = round(v*k), exact halving, add (separable.cu:581-584).  Halving
+// commutes with the rounding of the product (a power-of-two scaling, barring underflow into the denormals, i.e. for
+// |v*k| >= 2^-125), so round(v * (k/2)) is the same number and the tap is one multiply and one add -- NOT an FMA, the
+// product is rounded on its own.  Two arrays share one FMUL2, (pl, ph) = (v0, v1) * (IL/2, IH/2), followed by two scalar
+// add.rn (ptxas contracts a packed mul.rn.f32x2 + add.rn.f32x2 pair into one FFMA2 even with --fmad=false, which would
+// round once: checked in the SASS).
 template <int HLEN>
+struct SwtHalfTaps {
+    float2 k[HLEN];   // (IL, IH)[hlen-1-j] / 2, exact
+};
+template <int HLEN, int F>
 __global__ void __launch_bounds__(kSwtThreads, 2)
-    k_swt_inv_fused(const __grid_constant__ Taps t, const float* __restrict__ A, size_t s_a, const float* __restrict__ H,
+    k_swt_inv_fused(const __grid_constant__ SwtHalfTaps<HLEN> t, const float* __restrict__ A, size_t s_a, const float* __restrict__ H,
                     const float* __restrict__ V, const float* __restrict__ D, size_t s_d, float* __restrict__ dst,
-                    size_t s_dst, int Nr, int Nc, int f)
+                    size_t s_dst, int Nr, int Nc, int f_rt)
 {
     using K = SwtInvCfg<HLEN>;
+    const int f = F ? F : f_rt;
+    auto khalf = [&](const int j) { return sw_pack2(t.k[j].x, t.k[j].y); };
     extern __shared__ __align__(16) float smem[];
     const int ci = K::TW + (HLEN - 1) * f;           // columns of t1/t2 the row pass of this tile reads
     float* S_c0 = smem;                              // A, then V
@@ -190,13 +235,15 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
                 for (int o = 0; o < K::RPT; o++) rl[o] = rh[o] = 0.f;
 #pragma unroll
                 for (int i = 0; i < K::RPT + HLEN - 1; i++) {
-                    const float v0 = S_c0[(m0 + i) * ci + u], v1 = S_c1[(m0 + i) * ci + u];
+                    const u64 v01 = sw_pack2(S_c0[(m0 + i) * ci + u], S_c1[(m0 + i) * ci + u]);
 #pragma unroll
                     for (int o = 0; o < K::RPT; o++) {
                         const int j = i - o;
                         if (j >= 0 && j < HLEN) {
-                            rl[o] = swt_acc(rl[o], v0, t.IL[HLEN - 1 - j]);
-                            rh[o] = swt_acc(rh[o], v1, t.IH[HLEN - 1 - j]);
+                            float pl, ph;   // the two products rounded on their own (one FMUL2), then two plain adds
+                            sw_unpack2(sw_fmul2(v01, khalf(j)), pl, ph);
+                            rl[o] = __fadd_rn(rl[o], pl);
+                            rh[o] = __fadd_rn(rh[o], ph);
                         }
                     }
                 }
@@ -220,8 +267,10 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
         float a1 = 0.f, a2 = 0.f;
 #pragma unroll
         for (int j = 0; j < HLEN; j++) {
-            a1 = swt_acc(a1, p1[j * f], t.IL[HLEN - 1 - j]);
-            a2 = swt_acc(a2, p2[j * f], t.IH[HLEN - 1 - j]);
+            float q1, q2;
+            sw_unpack2(sw_fmul2(sw_pack2(p1[j * f], p2[j * f]), khalf(j)), q1, q2);
+            a1 = __fadd_rn(a1, q1);
+            a2 = __fadd_rn(a2, q2);
         }
         const int gy = ry + f * (mt * K::TH + m);
         if (gy < Nr && gx < Nc) dst[(size_t)gy * Nc + gx] = __fadd_rn(a1, a2);
@@ -238,17 +287,29 @@ static int launch_swt_fwd(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 
     const size_t smem = K::smem(f);
     // the reference's single wrap must suffice (it does for every level the Wavelets class allows) and the tile must fit
     if (smem > kSwtSmemCap || (HLEN - 1) * f >= Nr || (HLEN - 1) * f >= Nc) return 0;
-    static size_t configured = 0;
-    if (smem > configured) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_swt_fwd_fused<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwtSmemCap));
-        configured = kSwtSmemCap;
-    }
     const int rows_per_class = idiv_up(Nr, f);
     dim3 grid(idiv_up(Nc, K::TW), f * idiv_up(rows_per_class, K::TH), batch);
     if (grid.y > 65535u) return 0;
     PDWT_PROF(prof_tag("k_swt_fwd_fused", Nr, f), s);
-    PDWT_CUDA(launch_pdl(k_swt_fwd_fused<HLEN>, grid, kSwtThreads, smem, s, t, (const float*)src.p, src.stride, A.p,
-                         A.stride, H.p, V.p, D.p, H.stride, Nr, Nc, f));
+#define PDWT_SWT_FWD(FF)                                                                                                 \
+    do {                                                                                                                 \
+        static bool configured = false;                                                                                  \
+        if (!configured) {                                                                                               \
+            PDWT_CUDA(cudaFuncSetAttribute(k_swt_fwd_fused<HLEN, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                           (int)kSwtSmemCap));                                                           \
+            configured = true;                                                                                           \
+        }                                                                                                                \
+        PDWT_CUDA(launch_pdl(k_swt_fwd_fused<HLEN, FF>, grid, kSwtThreads, smem, s, t, (const float*)src.p, src.stride,  \
+                             A.p, A.stride, H.p, V.p, D.p, H.stride, Nr, Nc, f));                                        \
+    } while (0)
+    switch (f) {
+        case 1: PDWT_SWT_FWD(1); break;
+        case 2: PDWT_SWT_FWD(2); break;
+        case 4: PDWT_SWT_FWD(4); break;
+        case 8: PDWT_SWT_FWD(8); break;
+        default: PDWT_SWT_FWD(0); break;
+    }
+#undef PDWT_SWT_FWD
     PDWT_LAUNCH_CHECK();
     return 1;
 }
@@ -261,17 +322,32 @@ static int launch_swt_inv(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D,
     const int f = 1 << (level - 1);
     const size_t smem = K::smem(f);
     if (smem > kSwtSmemCap || (HLEN - 1) * f >= Nr || (HLEN - 1) * f >= Nc) return 0;
-    static size_t configured = 0;
-    if (smem > configured) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_swt_inv_fused<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwtSmemCap));
-        configured = kSwtSmemCap;
-    }
     const int rows_per_class = idiv_up(Nr, f);
     dim3 grid(idiv_up(Nc, K::TW), f * idiv_up(rows_per_class, K::TH), batch);
     if (grid.y > 65535u) return 0;
     PDWT_PROF(prof_tag("k_swt_inv_fused", Nr, f), s);
-    PDWT_CUDA(launch_pdl(k_swt_inv_fused<HLEN>, grid, kSwtThreads, smem, s, t, (const float*)A.p, A.stride,
-                         (const float*)H.p, (const float*)V.p, (const float*)D.p, H.stride, dst.p, dst.stride, Nr, Nc, f));
+    SwtHalfTaps<HLEN> ht;
+    for (int j = 0; j < HLEN; j++) ht.k[j] = make_float2(t.IL[HLEN - 1 - j] * 0.5f, t.IH[HLEN - 1 - j] * 0.5f);
+#define PDWT_SWT_INV(FF)                                                                                                 \
+    do {                                                                                                                 \
+        static bool configured = false;                                                                                  \
+        if (!configured) {                                                                                               \
+            PDWT_CUDA(cudaFuncSetAttribute(k_swt_inv_fused<HLEN, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                           (int)kSwtSmemCap));                                                           \
+            configured = true;                                                                                           \
+        }                                                                                                                \
+        PDWT_CUDA(launch_pdl(k_swt_inv_fused<HLEN, FF>, grid, kSwtThreads, smem, s, ht, (const float*)A.p, A.stride,     \
+                             (const float*)H.p, (const float*)V.p, (const float*)D.p, H.stride, dst.p, dst.stride, Nr,   \
+                             Nc, f));                                                                                    \
+    } while (0)
+    switch (f) {
+        case 1: PDWT_SWT_INV(1); break;
+        case 2: PDWT_SWT_INV(2); break;
+        case 4: PDWT_SWT_INV(4); break;
+        case 8: PDWT_SWT_INV(8); break;
+        default: PDWT_SWT_INV(0); break;
+    }
+#undef PDWT_SWT_INV
     PDWT_LAUNCH_CHECK();
     return 1;
 }
