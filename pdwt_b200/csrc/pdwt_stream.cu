@@ -134,6 +134,9 @@ __device__ __forceinline__ void cp_async_mbar_arrive(unsigned bar)
 
 constexpr int round4(int n) { return (n + 3) & ~3; }
 
+// dynamic shared memory that lets exactly two CTAs share an SM (228 KB per SM, 1 KB reserved per CTA)
+constexpr size_t kTwoPerSmBytes = 112 * 1024;
+
 static int sm_count()
 {
     static const int n = []() {
@@ -238,8 +241,12 @@ __device__ __forceinline__ void tl_stamp(int cta, int slot)
 #define TL(slot, cond) do { } while (0)
 #endif
 
-template <int HLEN>
-__global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) k_fwd2d_stream(const __grid_constant__ FwdParams<HLEN> p)
+// LOWOCC: variant for grids that put at most 2 CTAs on an SM anyway (one image): it may use twice the registers, which
+// buys an earlier prefetch of the next pair's first row (its shared-memory latency hides behind the second row's FFMA2s
+// instead of sitting at the head of the next iteration; with the 4-CTA register budget that spills).
+template <int HLEN, bool LOWOCC>
+__global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 14 ? 4 : 3))
+    k_fwd2d_stream(const __grid_constant__ FwdParams<HLEN> p)
 {
     using G = FwdGeom<HLEN>;
     constexpr int H2 = G::H2, NC = G::NC, NSS = G::NSS, SR = G::SR, NCW = G::NCW;
@@ -345,7 +352,13 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
             TL(2, lane == 0 && next[0] == 1 && remaining == nstrips * (nss - 1));
             if (!any) __nanosleep(40);
         }
-        TL(7, lane == 0);
+#ifdef PDWT_EXPERIMENTS
+        if (lane == 0 && blockIdx.x < 1024) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_timeline[blockIdx.x * 8 + 7] = smid;   // slot 7: the SM this CTA ran on
+        }
+#endif
         return;
     }
 
@@ -434,11 +447,26 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
             unsigned ready = 1;
             if (last_in_ss && more) ready = mbar_test(nbar, nparity);
             row_step(xa, sb, 0);
+            const bool arrive_now = last_in_ss;
+            const unsigned cur_bar = bar;
+            auto advance = [&]() {   // ring position of the next pair, then its first row into xa
+                if (last_in_ss) {
+                    if (!ready) mbar_wait(nbar, nparity);
+                    soff = nsoff;
+                    bar = nbar;
+                    parity = nparity;
+                    pin = 0;
+                } else {
+                    pin++;
+                }
+                load_row(xa, lane_ring + soff + pin * (2 * G::WW * 4));
+            };
+            if (LOWOCC && more) advance();   // xa is consumed: prefetch now
             row_step(xb, sb, 1);
-            if (last_in_ss) {
+            if (arrive_now) {
                 // every lane has consumed all rows of this super-slot: hand it back to the producer
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar + 8);
+                if (lane == 0) mbar_arrive(cur_bar + 8);
             }
             TL(4, q == 0 && threadIdx.x == 0);
             TL(5, q == H2 - 1 && threadIdx.x == 0);
@@ -463,16 +491,7 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, (HLEN <= 14 ? 4 : 3)) 
                 return;
             }
             q++;
-            if (last_in_ss) {
-                if (!ready) mbar_wait(nbar, nparity);
-                soff = nsoff;
-                bar = nbar;
-                parity = nparity;
-                pin = 0;
-            } else {
-                pin++;
-            }
-            load_row(xa, lane_ring + soff + pin * (2 * G::WW * 4));
+            if (!LOWOCC) advance();
         }
     }
 }
@@ -507,10 +526,12 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
     if ((((uintptr_t)src.p) & 15) || (src.stride & 3)) return 0;
     if ((((uintptr_t)A.p | (uintptr_t)H.p | (uintptr_t)V.p | (uintptr_t)D.p) & 7) || (A.stride & 1) || (H.stride & 1))
         return 0;
-    static int per_sm = 0;   // resident CTAs per SM
+    static int per_sm = 0;   // resident CTAs per SM (standard variant)
     if (!per_sm) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_fwd2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd2d_stream<HLEN>, G::THREADS, G::SMEM) != cudaSuccess || per_sm < 1) {
+        PDWT_CUDA(cudaFuncSetAttribute(k_fwd2d_stream<HLEN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        PDWT_CUDA(cudaFuncSetAttribute(k_fwd2d_stream<HLEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(G::SMEM > kTwoPerSmBytes ? G::SMEM : kTwoPerSmBytes)));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd2d_stream<HLEN, false>, G::THREADS, G::SMEM) != cudaSuccess || per_sm < 1) {
             cudaGetLastError();
             per_sm = 3;
         }
@@ -562,11 +583,20 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
     if (const char* e = getenv("PDWT_TH")) TH = atoi(e) > 0 ? atoi(e) : TH;
     p.TH = TH;
     p.nrc = idiv_up(nr, TH);
-    p.pdl_early = pdl_mode() == 1;
     const long long nctas = (long long)p.ncg * p.nrc * batch;
     if (nctas > 0x7fffffff) return 0;
     PDWT_PROF(prof_tag("k_fwd2d_stream", Nr, Nc), s);
-    PDWT_CUDA(launch_pdl(k_fwd2d_stream<HLEN>, dim3((unsigned)nctas), G::THREADS, G::SMEM, s, p));
+    // at most 2 CTAs per SM: the high-register variant loses no occupancy (PDWT_LOWOCC=0|1 forces the choice)
+    bool lowocc = nctas <= 2LL * sm_count();
+    if (const char* e = getenv("PDWT_LOWOCC")) lowocc = atoi(e) != 0;
+    // ... and it asks for so much shared memory that NO SM can take a third CTA: the block scheduler does not spread a
+    // grid of 2 x SMs CTAs evenly by itself, and the kernel ends with the busiest SM (PDWT_TWOPERSM=0 switches it off)
+    static const bool cap2 = []() { const char* e = getenv("PDWT_TWOPERSM"); return !e || atoi(e) != 0; }();
+    if (lowocc)
+        PDWT_CUDA(launch_pdl(k_fwd2d_stream<HLEN, true>, dim3((unsigned)nctas), G::THREADS,
+                             cap2 && G::SMEM < kTwoPerSmBytes ? kTwoPerSmBytes : G::SMEM, s, p));
+    else
+        PDWT_CUDA(launch_pdl(k_fwd2d_stream<HLEN, false>, dim3((unsigned)nctas), G::THREADS, G::SMEM, s, p));
     PDWT_LAUNCH_CHECK();
     return 1;
 }
