@@ -89,6 +89,7 @@ class Wavelets {
     double* d_sums;   // device scratch of the norm reductions
     double* h_sums;   // pinned host mirror
     long long launches;
+    int norm_cache;   // bit 0 / 1: the L1 / L2 sums of the current coefficients are in d_sums (left by a threshold)
     int alloc_buffers();
     void free_buffers();
     int norms(int mode, DTYPE* out);

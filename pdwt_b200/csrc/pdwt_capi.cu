@@ -617,7 +617,7 @@ namespace {
 int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with_details, bool with_app,
                   const float* beta_levels, float beta_app, int op /*0 soft,1 hard,2 asum,3 sumsq,4 proj_linf,5 scale*/,
                   double* d_sums,
-                  int* nseg_out)
+                  int* nseg_out, bool app_readonly = false)
 {
     SegTable tab;
     memset(&tab, 0, sizeof tab);
@@ -626,7 +626,7 @@ int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with
         if (tab.nseg == 0) return 0;
         int rc;
         if (op < 2)
-            rc = e_threshold(tab, op, batch, s);
+            rc = e_threshold(tab, op, batch, s, d_sums);   // d_sums != NULL: the norms of the result come with it
         else if (op < 4)
             rc = e_reduce(tab, op - 2, batch, d_sums, s);
         else
@@ -638,12 +638,13 @@ int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with
         int r, cdim;
         if (pdwt_coeff_dims(w, k, &r, &cdim) != PDWT_OK) return PDWT_ERR_ARG;
         if (!c[k]) return PDWT_ERR_ARG;
-        if ((op == 2 || op == 3) && tab.nseg == kMaxSeg) return PDWT_ERR_ARG;  // reductions need one table (sums layout)
+        if ((op == 2 || op == 3 || d_sums) && tab.nseg == kMaxSeg) return PDWT_ERR_ARG;  // sums need ONE table (layout)
         if (tab.nseg == kMaxSeg) TRY(flush());
         tab.ptr[tab.nseg] = c[k];
         tab.n[tab.nseg] = (unsigned long long)r * cdim;
         tab.stride[tab.nseg] = pdwt_coeff_alloc_elems(w, k);
         tab.beta[tab.nseg] = beta;
+        tab.ro[tab.nseg] = (k == 0 && app_readonly) ? 1 : 0;
         tab.nseg++;
         total++;
         return 0;
@@ -657,10 +658,17 @@ int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with
     return flush();
 }
 
-// w_call_soft_thresh / w_call_hard_thresh, common.cu:219-282
-int threshold_impl(float** c, float beta, pdwt_w_info w, int app, int normalize, int batch, cudaStream_t s, int hard)
+// w_call_soft_thresh / w_call_hard_thresh, common.cu:219-282.  d_sums2 != NULL (2 * batch * ncoeffs doubles on the device):
+// the same launch leaves sum |c| and sum c^2 of every sub-band AFTER the threshold there, A_L included (read-only when
+// it is not thresholded) -- SURVEY 8f N1.
+int threshold_impl(float** c, float beta, pdwt_w_info w, int app, int normalize, int batch, cudaStream_t s, int hard,
+                   double* d_sums2 = nullptr)
 {
     if (!c || w.nlevels < 1 || w.nlevels > 32 || batch < 1) return PDWT_ERR_ARG;
+    if (d_sums2) {
+        if (pdwt_num_coeffs(w) > kMaxSeg) d_sums2 = nullptr;
+        else PDWT_CUDA(cudaMemsetAsync(d_sums2, 0, sizeof(double) * 2 * batch * pdwt_num_coeffs(w), s));
+    }
     float beta_app = beta;
     if (app && !hard && normalize > 0) {  // beta2 = beta / sqrt(2)^nlevels (soft only; hard passes beta, common.cu:270)
         const int half = w.nlevels / 2;
@@ -672,6 +680,7 @@ int threshold_impl(float** c, float beta, pdwt_w_info w, int app, int normalize,
         if (normalize > 0) beta = (float)((double)beta / 1.4142135623730951);  // common.cu:244 (SQRT_2 is a double)
         bl[l] = beta;
     }
+    if (d_sums2) return launch_tables(c, w, batch, s, true, true, bl, beta_app, hard ? 1 : 0, d_sums2, nullptr, app == 0);
     return launch_tables(c, w, batch, s, true, app != 0, bl, beta_app, hard ? 1 : 0, nullptr, nullptr);
 }
 
@@ -714,6 +723,13 @@ int group_soft_impl(float** c, float beta, pdwt_w_info w, int app, int normalize
 }  // namespace
 
 namespace pdwt {
+int norm_finish(pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, const double* d_sums, double* h_sums);
+// thresholds of the Wavelets object: d_sums2 receives the norms of the result (see threshold_impl)
+int threshold_norms(float** c, float beta, pdwt_w_info w, int app, int normalize, int batch, cudaStream_t s, int hard,
+                    double* d_sums2)
+{
+    return threshold_impl(c, beta, w, app, normalize, batch, s, hard, d_sums2);
+}
 // shared with the Wavelets object: reduction with caller-provided scratch (d_sums/h_sums: batch*kMaxSeg doubles)
 int norm_impl(float** c, pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, double* d_sums, double* h_sums)
 {
@@ -723,9 +739,16 @@ int norm_impl(float** c, pdwt_w_info w, int batch, int mode, float* out, cudaStr
     PDWT_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * batch * nseg, s));
     int pushed = 0;
     TRY(launch_tables(c, w, batch, s, true, true, nullptr, 0.f, 2 + mode, d_sums, &pushed));
+    return norm_finish(w, batch, mode, out, s, d_sums, h_sums);
+}
+
+// the sums are on the device (one double per plane and sub-band, details first, A last): fetch them and accumulate in
+// float, sub-band by sub-band in the reference's order (wt.cu:373-394, 400-417)
+int norm_finish(pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, const double* d_sums, double* h_sums)
+{
+    const int nseg = pdwt_num_coeffs(w);
     PDWT_CUDA(cudaMemcpyAsync(h_sums, d_sums, sizeof(double) * batch * nseg, cudaMemcpyDeviceToHost, s));
     PDWT_CUDA(cudaStreamSynchronize(s));
-    // host accumulation in float, sub-band by sub-band in the reference's order (wt.cu:373-394, 400-417)
     for (int p = 0; p < batch; p++) {
         float res = 0.0f;
         for (int k = 0; k < nseg; k++) {

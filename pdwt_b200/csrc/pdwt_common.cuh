@@ -177,8 +177,12 @@ struct SegTable {  // list of (sub-band, length, parameter) handled by one launc
     unsigned long long n[kMaxSeg];       // floats per plane to process
     unsigned long long stride[kMaxSeg];  // floats between planes
     float beta[kMaxSeg];
+    unsigned char ro[kMaxSeg];           // 1: the element-wise kernels only READ this segment (it is there for its norm)
 };
-int e_threshold(const SegTable& tab, int op /*0 soft, 1 hard, 2 proj_linf, 3 scale by beta*/, int batch, cudaStream_t s);
+// sums != NULL: the kernel also accumulates sum |out| into sums[plane*nseg + seg] and sum out^2 into
+// sums[batch*nseg + plane*nseg + seg] (the norm of the thresholded coefficients comes for free)
+int e_threshold(const SegTable& tab, int op /*0 soft, 1 hard, 2 proj_linf, 3 scale by beta*/, int batch, cudaStream_t s,
+                double* sums = nullptr);
 struct GroupTable {  // group soft threshold: per level the detail triple (h, v NULL in 1-D) and, optionally, A
     int nlev;
     float *h[32], *v[32], *d[32], *a[32];

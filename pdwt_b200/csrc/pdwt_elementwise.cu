@@ -26,8 +26,8 @@ __device__ __forceinline__ float ew1(float v, float beta)
     return OP == 0 ? soft1(v, beta) : OP == 1 ? hard1(v, beta) : OP == 2 ? linf1(v, beta) : __fmul_rn(beta, v);
 }
 
-template <int OP>
-__global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTable tab)
+template <int OP, bool SUMS>
+__global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTable tab, double* __restrict__ sums, int batch)
 {
     const int seg = blockIdx.y;
     float* p = tab.ptr[seg] + (size_t)blockIdx.z * tab.stride[seg];
@@ -42,22 +42,77 @@ __global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTa
     if (blockIdx.x >= nb) return;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = nb * blockDim.x;
     float4* pv = reinterpret_cast<float4*>(p + head);
+    const bool ro = tab.ro[seg] != 0;   // read-only segment: only its sums are wanted
+    double s1 = 0.0, s2 = 0.0;          // sum |out|, sum out^2 (SUMS); per vector in float like k_reduce, then double
     auto apply = [&](float4 v) {
-        v.x = ew1<OP>(v.x, beta); v.y = ew1<OP>(v.y, beta); v.z = ew1<OP>(v.z, beta); v.w = ew1<OP>(v.w, beta);
+        if (!ro) {
+            v.x = ew1<OP>(v.x, beta); v.y = ew1<OP>(v.y, beta); v.z = ew1<OP>(v.z, beta); v.w = ew1<OP>(v.w, beta);
+        }
+        if (SUMS) {
+            s1 += (double)((fabsf(v.x) + fabsf(v.y)) + (fabsf(v.z) + fabsf(v.w)));
+            s2 += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+        }
+        return v;
+    };
+    auto apply1 = [&](float v) {
+        if (!ro) v = ew1<OP>(v, beta);
+        if (SUMS) {
+            s1 += (double)fabsf(v);
+            s2 += (double)(v * v);
+        }
         return v;
     };
     size_t i = tid;
     for (; i + 3 * nth < nvec; i += 4 * nth) {   // four independent 128-bit loads in flight per thread
-        const float4 a = pv[i], b = pv[i + nth], c = pv[i + 2 * nth], d = pv[i + 3 * nth];
-        pv[i] = apply(a);
-        pv[i + nth] = apply(b);
-        pv[i + 2 * nth] = apply(c);
-        pv[i + 3 * nth] = apply(d);
+        const float4 a = apply(pv[i]), b = apply(pv[i + nth]), c = apply(pv[i + 2 * nth]), d = apply(pv[i + 3 * nth]);
+        if (!ro) {
+            pv[i] = a;
+            pv[i + nth] = b;
+            pv[i + 2 * nth] = c;
+            pv[i + 3 * nth] = d;
+        }
     }
-    for (; i < nvec; i += nth) pv[i] = apply(pv[i]);
-    if (tid < head) p[tid] = ew1<OP>(p[tid], beta);
+    for (; i < nvec; i += nth) {
+        const float4 a = apply(pv[i]);
+        if (!ro) pv[i] = a;
+    }
+    if (tid < head) {
+        const float a = apply1(p[tid]);
+        if (!ro) p[tid] = a;
+    }
     const size_t tail0 = head + (nvec << 2);
-    if (tail0 + tid < n) p[tail0 + tid] = ew1<OP>(p[tail0 + tid], beta);
+    if (tail0 + tid < n) {
+        const float a = apply1(p[tail0 + tid]);
+        if (!ro) p[tail0 + tid] = a;
+    }
+    if (SUMS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        __shared__ double w1[8], w2[8];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) {
+            w1[wid] = s1;
+            w2[wid] = s2;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            s1 = lane < 8 ? w1[lane] : 0.0;
+            s2 = lane < 8 ? w2[lane] : 0.0;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (lane == 0) {
+                const size_t k = (size_t)blockIdx.z * tab.nseg + seg;
+                atomicAdd(&sums[k], s1);
+                atomicAdd(&sums[(size_t)batch * tab.nseg + k], s2);
+            }
+        }
+    }
 }
 
 // sum |v| (MODE 0) or sum v^2 (MODE 1): per-thread double accumulation of float4 loads, warp shuffle tree,
@@ -115,16 +170,25 @@ static int blocks_for(const SegTable& tab, int per_sm = 4)
     return (int)b;
 }
 
-int e_threshold(const SegTable& tab, int op, int batch, cudaStream_t s)
+int e_threshold(const SegTable& tab, int op, int batch, cudaStream_t s, double* sums)
 {
     PDWT_PROF(__func__, s);
     if (tab.nseg == 0) return 0;
-    dim3 grid(blocks_for(tab), tab.nseg, batch);
-    switch (op) {
-        case 0: k_threshold<0><<<grid, 256, 0, s>>>(tab); break;
-        case 1: k_threshold<1><<<grid, 256, 0, s>>>(tab); break;
-        case 2: k_threshold<2><<<grid, 256, 0, s>>>(tab); break;
-        default: k_threshold<3><<<grid, 256, 0, s>>>(tab); break;
+    dim3 grid(blocks_for(tab, sums ? 2 : 4), tab.nseg, batch);
+    if (sums) {   // thresholds that also deliver the norms of their result
+        switch (op) {
+            case 0: k_threshold<0, true><<<grid, 256, 0, s>>>(tab, sums, batch); break;
+            case 1: k_threshold<1, true><<<grid, 256, 0, s>>>(tab, sums, batch); break;
+            case 2: k_threshold<2, true><<<grid, 256, 0, s>>>(tab, sums, batch); break;
+            default: k_threshold<3, true><<<grid, 256, 0, s>>>(tab, sums, batch); break;
+        }
+    } else {
+        switch (op) {
+            case 0: k_threshold<0, false><<<grid, 256, 0, s>>>(tab, nullptr, batch); break;
+            case 1: k_threshold<1, false><<<grid, 256, 0, s>>>(tab, nullptr, batch); break;
+            case 2: k_threshold<2, false><<<grid, 256, 0, s>>>(tab, nullptr, batch); break;
+            default: k_threshold<3, false><<<grid, 256, 0, s>>>(tab, nullptr, batch); break;
+        }
     }
     PDWT_LAUNCH_CHECK();
     return 0;

@@ -13,6 +13,9 @@
 
 namespace pdwt {
 int norm_impl(float** c, pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, double* d_sums, double* h_sums);
+int norm_finish(pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, const double* d_sums, double* h_sums);
+int threshold_norms(float** c, float beta, pdwt_w_info w, int app, int normalize, int batch, cudaStream_t s, int hard,
+                    double* d_sums2);
 }
 using namespace pdwt;
 
@@ -27,11 +30,18 @@ using namespace pdwt;
     } while (0)
 
 static int cuda_rc(cudaError_t e) { return note_cuda(e); }
+// PDWT_NORM_CACHE=0: norm1()/norm2sq() always re-read the coefficients (for callers that write into the sub-bands through
+// coeff_int_ptr() between a threshold and a norm, which no method of the class can see)
+static bool norm_cache_enabled()
+{
+    const char* e = getenv("PDWT_NORM_CACHE");
+    return !e || atoi(e) != 0;
+}
 
 Wavelets::Wavelets()
     : d_image(NULL), d_coeffs(NULL), d_tmp(NULL), current_shift_r(0), current_shift_c(0), do_separable(1),
       do_cycle_spinning(0), state(W_INIT), batch(1), last_error(0), stream(NULL), async_copies(0), filters(NULL),
-      d_sums(NULL), h_sums(NULL), launches(0)
+      d_sums(NULL), h_sums(NULL), launches(0), norm_cache(0)
 {
     memset(wname, 0, sizeof wname);
     memset(&winfos, 0, sizeof winfos);
@@ -43,7 +53,7 @@ int Wavelets::alloc_buffers()
     int rc;
     if ((rc = cuda_rc(cudaMalloc(&d_image, sizeof(DTYPE) * plane * batch))) < 0) return rc;
     if ((rc = cuda_rc(cudaMalloc(&d_tmp, sizeof(DTYPE) * 2 * plane * batch))) < 0) return rc;  // wt.cu:128-130
-    if ((rc = cuda_rc(cudaMalloc(&d_sums, sizeof(double) * kMaxSeg * batch))) < 0) return rc;
+    if ((rc = cuda_rc(cudaMalloc(&d_sums, sizeof(double) * 3 * kMaxSeg * batch))) < 0) return rc;
     if ((rc = cuda_rc(cudaMallocHost(&h_sums, sizeof(double) * kMaxSeg * batch))) < 0) return rc;
     return PDWT_OK;
 }
@@ -73,7 +83,7 @@ Wavelets::Wavelets(DTYPE* img, int Nr, int Nc, const char* name, int levels, int
                    int do_cycle_spinning_, int do_swt, int ndim, int batch_)
     : d_image(NULL), d_coeffs(NULL), d_tmp(NULL), current_shift_r(0), current_shift_c(0), do_separable(do_separable_),
       do_cycle_spinning(do_cycle_spinning_), state(W_INIT), batch(batch_ < 1 ? 1 : batch_), last_error(0), stream(NULL),
-      async_copies(0), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0)
+      async_copies(0), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0), norm_cache(0)
 {
     memset(wname, 0, sizeof wname);
     winfos.Nr = Nr;
@@ -173,7 +183,7 @@ Wavelets::Wavelets(DTYPE* img, int Nr, int Nc, const char* name, int levels, int
 Wavelets::Wavelets(const Wavelets& W)
     : d_image(NULL), d_coeffs(NULL), d_tmp(NULL), current_shift_r(W.current_shift_r), current_shift_c(W.current_shift_c),
       do_separable(W.do_separable), do_cycle_spinning(W.do_cycle_spinning), winfos(W.winfos), state(W.state),
-      batch(W.batch), last_error(0), stream(W.stream), async_copies(W.async_copies), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0)
+      batch(W.batch), last_error(0), stream(W.stream), async_copies(W.async_copies), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0), norm_cache(0)
 {
     memcpy(wname, W.wname, sizeof wname);
     if (winfos.Nr < 1 || winfos.Nc < 1) return;
@@ -216,6 +226,7 @@ void Wavelets::forward()
         puts("Warning: forward transform not computed, as there was an error when creating the wavelets");
         return;
     }
+    norm_cache = 0;
     const long long before = pdwt_launch_count();
     if (do_cycle_spinning) {   // wt.cu:242-246: a random circular shift of the image before the transform
         current_shift_r = rand() % winfos.Nr;
@@ -239,6 +250,7 @@ void Wavelets::inverse()
         puts("Warning: inverse transform not computed, as there was an error in a previous stage");
         return;
     }
+    norm_cache = 0;
     const long long before = pdwt_launch_count();
     W_TRY(pdwt_inverse(filters, d_image, d_coeffs, d_tmp, winfos, batch, stream, do_separable), W_INVERSE_ERROR);
     if (do_cycle_spinning)     // wt.cu:305: shift back
@@ -257,8 +269,13 @@ void Wavelets::soft_threshold(DTYPE beta, int do_thresh_appcoeffs, int normalize
     }
     if (state == W_CREATION_ERROR) return;
     const long long before = pdwt_launch_count();
-    W_TRY(pdwt_call_soft_thresh(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, stream),
+    // the same launch leaves the L1 / L2 norms of the thresholded coefficients in d_sums (second and third block): a
+    // norm1() / norm2sq() that follows needs no pass over the coefficients
+    norm_cache = 0;
+    W_TRY(threshold_norms(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, (cudaStream_t)stream, 0,
+                          d_sums + (size_t)kMaxSeg * batch),
           W_THRESHOLD_ERROR);
+    norm_cache = (pdwt_num_coeffs(winfos) <= kMaxSeg && norm_cache_enabled()) ? 3 : 0;
     launches += pdwt_launch_count() - before;
 }
 
@@ -271,8 +288,11 @@ void Wavelets::hard_threshold(DTYPE beta, int do_thresh_appcoeffs, int normalize
     }
     if (state == W_CREATION_ERROR) return;
     const long long before = pdwt_launch_count();
-    W_TRY(pdwt_call_hard_thresh(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, stream),
+    norm_cache = 0;
+    W_TRY(threshold_norms(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, (cudaStream_t)stream, 1,
+                          d_sums + (size_t)kMaxSeg * batch),
           W_THRESHOLD_ERROR);
+    norm_cache = (pdwt_num_coeffs(winfos) <= kMaxSeg && norm_cache_enabled()) ? 3 : 0;
     launches += pdwt_launch_count() - before;
 }
 
@@ -284,6 +304,7 @@ void Wavelets::group_soft_threshold(DTYPE beta, int do_thresh_appcoeffs, int nor
         return;
     }
     if (state == W_CREATION_ERROR) return;
+    norm_cache = 0;
     const long long before = pdwt_launch_count();
     W_TRY(pdwt_call_group_soft_thresh(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, stream),
           W_THRESHOLD_ERROR);
@@ -298,6 +319,7 @@ void Wavelets::shrink(DTYPE beta, int do_thresh_appcoeffs)
         return;
     }
     if (state == W_CREATION_ERROR) return;
+    norm_cache = 0;
     const long long before = pdwt_launch_count();
     W_TRY(pdwt_shrink(d_coeffs, beta, winfos, do_thresh_appcoeffs, batch, stream), W_THRESHOLD_ERROR);
     launches += pdwt_launch_count() - before;
@@ -311,6 +333,7 @@ void Wavelets::proj_linf(DTYPE beta, int do_thresh_appcoeffs)
         return;
     }
     if (state == W_CREATION_ERROR) return;
+    norm_cache = 0;
     const long long before = pdwt_launch_count();
     W_TRY(pdwt_call_proj_linf(d_coeffs, beta, winfos, do_thresh_appcoeffs, batch, stream), W_THRESHOLD_ERROR);
     launches += pdwt_launch_count() - before;
@@ -354,6 +377,7 @@ int Wavelets::add_wavelet_ref(const Wavelets& W, DTYPE alpha)
     if (!d_coeffs || !W.d_coeffs) return -2;
     if (W.stream != stream) cudaStreamSynchronize((cudaStream_t)W.stream);   // the operand's pending work
     const long long before = pdwt_launch_count();
+    norm_cache = 0;
     const int rc = pdwt_add_coeffs(d_coeffs, W.d_coeffs, winfos, alpha, batch, stream);
     launches += pdwt_launch_count() - before;
     if (rc < 0) {
@@ -367,7 +391,12 @@ int Wavelets::norms(int mode, DTYPE* out)
 {
     if (state == W_CREATION_ERROR || !d_coeffs) return PDWT_ERR_STATE;
     const long long before = pdwt_launch_count();
-    const int rc = norm_impl(d_coeffs, winfos, batch, mode, out, (cudaStream_t)stream, d_sums, h_sums);
+    int rc;
+    if (norm_cache & (1 << mode))   // left behind by the last threshold: [kMaxSeg*batch + mode*batch*ncoeffs ...]
+        rc = norm_finish(winfos, batch, mode, out, (cudaStream_t)stream,
+                         d_sums + (size_t)kMaxSeg * batch + (size_t)mode * batch * pdwt_num_coeffs(winfos), h_sums);
+    else
+        rc = norm_impl(d_coeffs, winfos, batch, mode, out, (cudaStream_t)stream, d_sums, h_sums);
     launches += pdwt_launch_count() - before;
     if (rc < 0) last_error = rc;
     return rc;
@@ -461,6 +490,7 @@ int Wavelets::get_coeff(DTYPE* coeff, int num)
 void Wavelets::set_coeff(DTYPE* coeff, int num, int mem_is_on_device)
 {
     if (!coeff) return;
+    norm_cache = 0;
     copy_coeff(this, coeff, num, mem_is_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, true);
 }
 

@@ -304,3 +304,33 @@ def test_async_copies_pipeline_over_streams():
         W.sync()
     for b, r in zip(h_out, ref):
         assert bitexact(b.numpy(), r)
+
+
+def test_norms_after_threshold_come_from_the_threshold_launch(monkeypatch):
+    """soft/hard_threshold leave the L1 / L2 sums of their result behind, so the norm that follows reads no
+    coefficients -- same values as a fresh reduction (1e-6), invalidated by everything that changes coefficients"""
+    L = pdwt_b200.lib()
+    for shape, wname, levels, kw in (((512, 768), "db7", 3, {}), ((96, 1000), "db4", 3, {"ndim": 1}),
+                                     ((128, 160), "sym4", 2, {"do_swt": 1}), ((3, 200, 264), "db3", 2, {})):
+        x = rnd(shape, 31)
+        for kind, app in (("soft", 0), ("soft", 1), ("hard", 0), ("hard", 1)):
+            W = Wavelets(x, wname, levels, **kw)
+            W.forward()
+            getattr(W, f"{kind}_threshold")(15.0, app, 1)
+            before = L.pdwt_launch_count()
+            n1, n2 = np.atleast_1d(W.norm1()), np.atleast_1d(W.norm2sq())
+            assert L.pdwt_launch_count() == before, "norms after a threshold must not launch a kernel"
+            monkeypatch.setenv("PDWT_NORM_CACHE", "0")
+            F = Wavelets(x, wname, levels, **kw)
+            F.forward()
+            getattr(F, f"{kind}_threshold")(15.0, app, 1)
+            f1, f2 = np.atleast_1d(F.norm1()), np.atleast_1d(F.norm2sq())
+            monkeypatch.delenv("PDWT_NORM_CACHE")
+            assert np.all(np.abs(n1 - f1) <= 1e-6 * np.abs(f1)) and np.all(np.abs(n2 - f2) <= 1e-6 * np.abs(f2)), (shape, kind, app)
+            for i in range(W.ncoeffs):
+                assert bitexact(W.get_coeff(i), F.get_coeff(i))
+            W.shrink(0.5)                                  # changes the coefficients: the cache must not survive
+            before = L.pdwt_launch_count()
+            s1 = np.atleast_1d(W.norm1())
+            assert L.pdwt_launch_count() > before
+            assert np.all(np.abs(s1 - f1 / np.float32(1.5)) <= 1e-5 * np.abs(f1))
