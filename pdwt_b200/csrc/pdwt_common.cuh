@@ -225,8 +225,7 @@ template <typename Kern, typename... Args>
 inline cudaError_t launch_pdl(Kern kern, dim3 grid, unsigned block, size_t smem, cudaStream_t s, const Args&... args)
 {
     const bool no_pdl = pdl_mode() == 0;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(block, 1, 1);
     cfg.dynamicSmemBytes = smem;

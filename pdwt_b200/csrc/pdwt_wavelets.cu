@@ -369,7 +369,7 @@ int Wavelets::add_wavelet_ref(const Wavelets& W, DTYPE alpha)
         puts("ERROR: add_wavelet(): operands should both use SWT or DWT");
         return -3;
     }
-    if ((do_cycle_spinning * W.do_cycle_spinning) &&
+    if ((do_cycle_spinning != 0 && W.do_cycle_spinning != 0) &&
         ((current_shift_r != W.current_shift_r) || (current_shift_c != W.current_shift_c))) {
         puts("ERROR: add_wavelet(): operands do not have the same current shift");
         return -4;
