@@ -117,8 +117,10 @@ __global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTa
 
 // sum |v| (MODE 0) or sum v^2 (MODE 1): per-thread double accumulation of float4 loads, warp shuffle tree,
 // one shared-memory pass across the 8 warps, one double atomicAdd per block.
+// (256, 4): without the bound ptxas took 96 registers, two blocks per SM, and the loads' latency showed (ncu: 8 cycles of
+// long_scoreboard per issue, 2.7 TB/s)
 template <int MODE>
-__global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ SegTable tab, double* __restrict__ sums)
+__global__ void __launch_bounds__(256, 4) k_reduce(const __grid_constant__ SegTable tab, double* __restrict__ sums)
 {
     const int seg = blockIdx.y;
     const float* p = tab.ptr[seg] + (size_t)blockIdx.z * tab.stride[seg];
@@ -134,12 +136,14 @@ __global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ SegTable
     auto term = [](float v) -> float { return MODE ? v * v : fabsf(v); };
     // the four terms of one vector are added in float (exact enough: 4 terms), the running sum in double
     auto vsum = [&](const float4 v) -> double { return (double)((term(v.x) + term(v.y)) + (term(v.z) + term(v.w))); };
-    size_t i = tid;
-    for (; i + 3 * nth < nvec; i += 4 * nth) {   // four independent 128-bit loads in flight per thread
-        const float4 a = __ldg(pv + i), b = __ldg(pv + i + nth), c = __ldg(pv + i + 2 * nth), d = __ldg(pv + i + 3 * nth);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = tid; i < nvec; i += 4 * nth) {   // four independent (guarded) 128-bit loads in flight per thread
+        const float4 a = __ldg(pv + i);
+        const float4 b = i + nth < nvec ? __ldg(pv + i + nth) : z4;
+        const float4 c = i + 2 * nth < nvec ? __ldg(pv + i + 2 * nth) : z4;
+        const float4 d = i + 3 * nth < nvec ? __ldg(pv + i + 3 * nth) : z4;
         acc += (vsum(a) + vsum(b)) + (vsum(c) + vsum(d));
     }
-    for (; i < nvec; i += nth) acc += vsum(__ldg(pv + i));
     if (tid < head) acc += (double)term(p[tid]);
     const size_t tail0 = head + (nvec << 2);
     if (tail0 + tid < n) acc += (double)term(p[tail0 + tid]);
@@ -295,7 +299,7 @@ int e_reduce(const SegTable& tab, int mode, int batch, double* d_sums, cudaStrea
 {
     PDWT_PROF(__func__, s);
     if (tab.nseg == 0) return 0;
-    dim3 grid(blocks_for(tab, 2), tab.nseg, batch);   // one double atomic per block: keep them few
+    dim3 grid(blocks_for(tab, 4), tab.nseg, batch);   // one double atomic per block: keep them few
     if (mode)
         k_reduce<1><<<grid, 256, 0, s>>>(tab, d_sums);
     else
