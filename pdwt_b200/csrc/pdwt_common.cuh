@@ -94,6 +94,24 @@ const char* prof_tag(const char* base, int rows, int cols);  // "base[rows x col
 
 inline int idiv_up(int a, int b) { return (a + b - 1) / b; }
 
+// Function attributes (dynamic shared memory limits) are per DEVICE: `static PerDeviceOnce once; if (once.first()) {...}`
+// runs its body the first time the call site is reached on each device of a process that uses several.
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    int dev = 0;
+    bool first()
+    {
+        dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) {
+            dev = 0;
+            return true;
+        }
+        if ((mask >> dev) & 1ull) return false;
+        mask |= 1ull << dev;
+        return true;
+    }
+};
+
 // level geometry of one plane
 inline int level_size(int N, int l, int do_swt)
 {

@@ -260,10 +260,9 @@ static int launch_ns_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
                          cudaStream_t s)
 {
     using K = NsFwdCfg<HLEN>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-        configured = true;
     }
     dim3 grid(idiv_up(half_up(Nc), K::TW), idiv_up(half_up(Nr), K::TH), batch);
     if (grid.y > 65535u) return 0;
@@ -280,10 +279,9 @@ static int launch_ns_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
 {
     using K = NsInvCfg<HLEN>;
     if (Nr < K::WIN || Nc < K::WIN) return 0;   // the single wrap must suffice
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_inv_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-        configured = true;
     }
     dim3 grid(idiv_up(Nc, K::TWC), idiv_up(Nr, K::THC), batch);
     if (grid.y > 65535u) return 0;

@@ -526,8 +526,11 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
     if ((((uintptr_t)src.p) & 15) || (src.stride & 3)) return 0;
     if ((((uintptr_t)A.p | (uintptr_t)H.p | (uintptr_t)V.p | (uintptr_t)D.p) & 7) || (A.stride & 1) || (H.stride & 1))
         return 0;
-    static int per_sm = 0;   // resident CTAs per SM (standard variant)
-    if (!per_sm) {
+    static PerDeviceOnce once;
+    static int per_sm_dev[64];   // resident CTAs per SM (standard variant), per device
+    const bool first = once.first();
+    int& per_sm = per_sm_dev[once.dev];
+    if (first) {
         PDWT_CUDA(cudaFuncSetAttribute(k_fwd2d_stream<HLEN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
         PDWT_CUDA(cudaFuncSetAttribute(k_fwd2d_stream<HLEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(G::SMEM > kTwoPerSmBytes ? G::SMEM : kTwoPerSmBytes)));
@@ -831,8 +834,11 @@ static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2
     // them (WIN-1 extra coefficient rows and the pipeline fill); items are spread over sms x per_sm resident warps, so
     // the kernel takes about ceil(items / slots) x (TM + 2.5): pick the TM that minimises it (4096^2: TM = 32, exactly
     // one item per slot).
-    static int per_sm = 0;
-    if (!per_sm) {
+    static PerDeviceOnce once;
+    static int per_sm_dev[64];
+    const bool first = once.first();
+    int& per_sm = per_sm_dev[once.dev];
+    if (first) {
         PDWT_CUDA(cudaFuncSetAttribute(k_inv2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv2d_stream<HLEN>, 32, G::SMEM) != cudaSuccess || per_sm < 1) {
             cudaGetLastError();
