@@ -14,8 +14,12 @@ JSON line (rank 0):
   value      Mpixels/s, device-resident inputs, CUDA events on the launching stream
   e2e        same metric through the public API with pinned HOST buffers: set_image (H2D) -> forward -> inverse
              -> get_image (D2H) inside the timed region
-  roofline   the dominant kernel (per-kernel CUDA-event pairs recorded by the library's profiler in a separate
-             pass over the same steps): algorithmic bytes per launch / average duration vs the measured HBM peak
+  e2e        ... `e2e.value`: 4 objects on 4 streams with set_async (copies and kernels of consecutive steps overlap);
+             `e2e.sync`: the reference's blocking calls
+  roofline   the dominant kernel (largest share of the step): algorithmic bytes per launch / average duration vs the
+             measured HBM peak, duration = one CUDA-event pair around every launch inside the steps (library profiler,
+             separate pass over the same steps); next to it the same kernel launched K times in a row between two
+             events, in plain stream order and with programmatic dependent launch
   cpu_baseline  the CPU oracle (port of the reference kernels, OpenMP) on this box's host cores, bounded sample
 `--impl reference` times the reference's own implementation: PDWT has no CPU path, its stock CUDA kernels compiled
 unmodified for sm_100 (oracle/_ref/libpdwt_ref.so, built by `make -C oracle ref`) run on the same GPU through the
@@ -274,42 +278,52 @@ def run_ours(args):
         kernels[e.name.decode()] = {"launches": e.launches, "avg_us": 1e3 * e.ms_total / e.launches,
                                     "min_us": 1e3 * e.ms_min, "total_ms": e.ms_total}
 
-    # ---- the level-1 kernels on their own: K back-to-back launches of ONE kernel between two events (the per-launch
-    # event pairs above add ~2.5 us of launch gap to every kernel and switch off the overlap of consecutive launches)
-    def back_to_back():
-        W1 = [Wavelets(torch.from_numpy(im).cuda(), wname, 1) for im in imgs]
-        for W in W1:
-            W.forward()
-        K = max(20, args.steps)
-        out = {}
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for i in range(K):
-            W1[i % ROT].forward()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        out["fwd_level1_us"] = round(1e3 * e0.elapsed_time(e1) / K, 2)
-        fh = C.c_void_p()
-        if L.pdwt_filters_create(C.byref(fh), wname.encode(), 0) > 0:
-            sets = []
+    # ---- the level-1 kernels on their own: K consecutive launches of ONE kernel between two events.  The per-launch
+    # event pairs above put an event record in front of every kernel: that adds 2-5 us of launch gap to each and breaks
+    # the programmatic-dependent-launch chain.  Two variants: PDWT_PDL=0 (plain stream order: launch n+1 starts when
+    # launch n has completed -- the kernel's own duration, used for `roofline`) and the library default (the next
+    # launch's prologue overlaps the tail of the previous one -- what a step sees).
+    def back_to_back(pdl_off):
+        if pdl_off:
+            os.environ["PDWT_PDL"] = "0"          # read by the library at every launch
+        try:
+            W1 = [Wavelets(torch.from_numpy(im).cuda(), wname, 1) for im in imgs]
             for W in W1:
-                cp = (C.c_void_p * W.ncoeffs)(*[W.coeff_int_ptr(k) for k in range(W.ncoeffs)])
-                sets.append((C.c_void_p(W.image_int_ptr()), cp, C.c_void_p(L.pdwt_wavelets_tmp_int_ptr(W._h)), W.info))
-            for img_p, cp, tmp_p, info in sets:
-                L.pdwt_inverse_separable(fh, img_p, cp, tmp_p, info, nimg, None)
+                W.forward()
+            K = max(20, args.steps)
+            out = {}
             torch.cuda.synchronize()
             e0.record(stream)
             for i in range(K):
-                img_p, cp, tmp_p, info = sets[i % ROT]
-                L.pdwt_inverse_separable(fh, img_p, cp, tmp_p, info, nimg, None)
+                W1[i % ROT].forward()
             e1.record(stream)
             torch.cuda.synchronize()
-            out["inv_level1_us"] = round(1e3 * e0.elapsed_time(e1) / K, 2)
-            L.pdwt_filters_destroy(fh)
-        out["launches_each"] = K
-        return out
+            out["fwd_level1_us"] = round(1e3 * e0.elapsed_time(e1) / K, 2)
+            fh = C.c_void_p()
+            if L.pdwt_filters_create(C.byref(fh), wname.encode(), 0) > 0:
+                sets = []
+                for W in W1:
+                    cp = (C.c_void_p * W.ncoeffs)(*[W.coeff_int_ptr(k) for k in range(W.ncoeffs)])
+                    sets.append((C.c_void_p(W.image_int_ptr()), cp, C.c_void_p(L.pdwt_wavelets_tmp_int_ptr(W._h)), W.info))
+                for img_p, cp, tmp_p, info in sets:
+                    L.pdwt_inverse_separable(fh, img_p, cp, tmp_p, info, nimg, None)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for i in range(K):
+                    img_p, cp, tmp_p, info = sets[i % ROT]
+                    L.pdwt_inverse_separable(fh, img_p, cp, tmp_p, info, nimg, None)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                out["inv_level1_us"] = round(1e3 * e0.elapsed_time(e1) / K, 2)
+                L.pdwt_filters_destroy(fh)
+            out["launches_each"] = K
+            return out
+        finally:
+            if pdl_off:
+                del os.environ["PDWT_PDL"]
 
-    b2b = back_to_back()
+    b2b = back_to_back(True)
+    b2b_pdl = back_to_back(False)
     peak, peak_src = peaks()
     roof = None
     if kernels:
@@ -317,17 +331,21 @@ def run_ours(args):
         ab = algorithmic_bytes(top)
         if ab:
             ab *= nimg
-            ach = ab / (kernels[top]["avg_us"] * 1e-6) / 1e9
+            key = "inv_level1_us" if "inv" in top else "fwd_level1_us"
+            dur_us = kernels[top]["avg_us"]      # one CUDA-event pair around every launch of it inside the steps
+            ach = ab / (dur_us * 1e-6) / 1e9
             roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": None, "algorithmic_bytes_per_launch": ab,
-                    "avg_us": round(kernels[top]["avg_us"], 2), "peak_source": peak_src,
+                    "avg_us": round(dur_us, 2), "peak_source": peak_src,
+                    "how": "average of one CUDA-event pair around every launch of this kernel inside the steps, on the "
+                           "launching stream (the event record in front of the launch adds part of the launch gap)",
                     "kernel_share_of_step": round(kernels[top]["total_ms"] / sum(v["total_ms"] for v in kernels.values()), 3)}
-            key = "inv_level1_us" if "inv" in top else "fwd_level1_us"
-            if key in b2b and top.endswith(f"[{Nr}x{Nc}]"):
-                roof["back_to_back"] = {"avg_us": b2b[key], "achieved": round(ab / (b2b[key] * 1e-6) / 1e9, 1),
-                                        "frac": round(ab / (b2b[key] * 1e-6) / 1e9 / peak, 4),
-                                        "how": f"{b2b['launches_each']} consecutive launches of this kernel alone between "
-                                               "two CUDA events, rotating buffers"}
+            if key in b2b and top.endswith(f"[{Nr}x{Nc}]"):   # the same kernel launched K times in a row, two events
+                for name, d, how in (("back_to_back", b2b, "plain stream order (PDWT_PDL=0): launch n+1 starts when n is complete"),
+                                     ("back_to_back_pdl", b2b_pdl, "library default: the next launch's prologue overlaps the tail")):
+                    roof[name] = {"avg_us": d[key], "frac": round(ab / (d[key] * 1e-6) / 1e9 / peak, 4),
+                                  "how": f"{d['launches_each']} consecutive launches of this kernel alone between two CUDA "
+                                         f"events, rotating buffers, {how}"}
             tr = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the ncu capture
             if os.path.exists(tr) and args.workload == "c2":
                 roof["traffic"] = json.load(open(tr)).get(top.split("[")[0])
@@ -361,7 +379,7 @@ def run_ours(args):
         "step_algorithmic_gbs": {"achieved": round(whole, 1), "frac_of_peak": round(whole / peak, 4),
                                  "bytes_per_pixel": 16},
         "kernels": {k: {"launches": v["launches"], "avg_us": round(v["avg_us"], 2)} for k, v in kernels.items()},
-        "level1_back_to_back": b2b,
+        "level1_back_to_back": {"plain_stream_order": b2b, "pdl": b2b_pdl},
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_port_baseline(Nr, Nc, wname, levels, iters=3)
