@@ -227,10 +227,10 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
 
 #ifdef PDWT_EXPERIMENTS
 // timeline instrumentation (PDWT_EXPERIMENTS builds only): 8 globaltimer stamps for each of the first 1024 CTAs
-__device__ unsigned long long g_timeline[1024 * 8];
+__device__ unsigned long long g_timeline[4096 * 8];
 __device__ __forceinline__ void tl_stamp(int cta, int slot)
 {
-    if (cta < 1024) {
+    if (cta < 4096) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_timeline[cta * 8 + slot] = t;
@@ -732,8 +732,10 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
     };
 #pragma unroll
     for (int i = 0; i < NSLOT; i++) wA[i] = wH[i] = wV[i] = wD[i] = 0ull;
+    TL(0, lane == 0);
     if (p.pdl_early) pdl_launch_dependents();
     pdl_wait();        // the previous level's kernel (or whatever wrote the coefficients) has completed
+    TL(1, lane == 0);
 #pragma unroll
     for (int i = 0; i < DEPTH; i++) issue_row(i);
 #pragma unroll
@@ -754,6 +756,15 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
     for (;;) {
 #pragma unroll
         for (int u = 0; u < UNR; u++) {       // body: UNR output row pairs; register, ring and tile indices all static
+#ifdef PDWT_EXPERIMENTS
+            if (s == 1) TL(3, lane == 0);
+            if (s >= nm && lane == 0 && blockIdx.x < 4096) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                g_timeline[blockIdx.x * 8 + 7] = smid;
+                tl_stamp(blockIdx.x, 6);
+            }
+#endif
             if (s >= nm) return;
             if (s + 1 >= nm) pdl_launch_dependents();
             if (s + 1 < nm) load_row(u + WIN);   // the row that the NEXT pair adds to the window (one pair of slack)
@@ -874,7 +885,7 @@ static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2
 }  // namespace pdwt
 extern "C" int pdwt_debug_timeline(unsigned long long* out, int n)
 {
-    if (n > 1024 * 8) n = 1024 * 8;
+    if (n > 4096 * 8) n = 4096 * 8;
     return (int)cudaMemcpyFromSymbol(out, pdwt::g_timeline, sizeof(unsigned long long) * n);
 }
 namespace pdwt {
