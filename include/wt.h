@@ -18,6 +18,8 @@
 
 #include "pdwt_b200.h"
 
+namespace pdwt { struct HostPublish; }   /* internal (csrc/pdwt_common.cuh) */
+
 #ifndef DTYPE
 #define DTYPE float /* reference filters.h:16-23 (single-precision build) */
 #endif
@@ -89,7 +91,10 @@ class Wavelets {
     double* d_sums;   // device scratch of the norm reductions
     double* h_sums;   // pinned host mirror
     long long launches;
-    int norm_cache;   // bit 0 / 1: the L1 / L2 sums of the current coefficients are in d_sums (left by a threshold)
+    int norm_cache;   // bit 0 / 1: the L1 / L2 sums of the current coefficients were published by the last threshold
+    double* h_sums_dev;            // device view of h_sums (mapped pinned memory)
+    unsigned thr_tag;              // tag that announces the last threshold's sums in h_sums
+    void publish_target(int which, pdwt::HostPublish* hp) const;
     int alloc_buffers();
     void free_buffers();
     int norms(int mode, DTYPE* out);

@@ -617,7 +617,7 @@ namespace {
 int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with_details, bool with_app,
                   const float* beta_levels, float beta_app, int op /*0 soft,1 hard,2 asum,3 sumsq,4 proj_linf,5 scale*/,
                   double* d_sums,
-                  int* nseg_out, bool app_readonly = false)
+                  int* nseg_out, bool app_readonly = false, const HostPublish* hp = nullptr)
 {
     SegTable tab;
     memset(&tab, 0, sizeof tab);
@@ -626,9 +626,9 @@ int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with
         if (tab.nseg == 0) return 0;
         int rc;
         if (op < 2)
-            rc = e_threshold(tab, op, batch, s, d_sums);   // d_sums != NULL: the norms of the result come with it
+            rc = e_threshold(tab, op, batch, s, d_sums, d_sums ? hp : nullptr);   // d_sums != NULL: the norms of the result come with it
         else if (op < 4)
-            rc = e_reduce(tab, op - 2, batch, d_sums, s);
+            rc = e_reduce(tab, op - 2, batch, d_sums, s, hp);
         else
             rc = e_threshold(tab, op - 2, batch, s);   // element-wise ops 2 (proj_linf) and 3 (scale)
         tab.nseg = 0;
@@ -661,13 +661,14 @@ int launch_tables(float** c, pdwt_w_info w, int batch, cudaStream_t s, bool with
 // w_call_soft_thresh / w_call_hard_thresh, common.cu:219-282.  d_sums2 != NULL (2 * batch * ncoeffs doubles on the device):
 // the same launch leaves sum |c| and sum c^2 of every sub-band AFTER the threshold there, A_L included (read-only when
 // it is not thresholded) -- SURVEY 8f N1.
+// hp != NULL: d_sums2 is zero on entry, the launch publishes the sums to the host and leaves it zero (HostPublish).
 int threshold_impl(float** c, float beta, pdwt_w_info w, int app, int normalize, int batch, cudaStream_t s, int hard,
-                   double* d_sums2 = nullptr)
+                   double* d_sums2 = nullptr, const HostPublish* hp = nullptr)
 {
     if (!c || w.nlevels < 1 || w.nlevels > 32 || batch < 1) return PDWT_ERR_ARG;
     if (d_sums2) {
         if (pdwt_num_coeffs(w) > kMaxSeg) d_sums2 = nullptr;
-        else PDWT_CUDA(cudaMemsetAsync(d_sums2, 0, sizeof(double) * 2 * batch * pdwt_num_coeffs(w), s));
+        else if (!hp) PDWT_CUDA(cudaMemsetAsync(d_sums2, 0, sizeof(double) * 2 * batch * pdwt_num_coeffs(w), s));
     }
     float beta_app = beta;
     if (app && !hard && normalize > 0) {  // beta2 = beta / sqrt(2)^nlevels (soft only; hard passes beta, common.cu:270)
@@ -680,7 +681,7 @@ int threshold_impl(float** c, float beta, pdwt_w_info w, int app, int normalize,
         if (normalize > 0) beta = (float)((double)beta / 1.4142135623730951);  // common.cu:244 (SQRT_2 is a double)
         bl[l] = beta;
     }
-    if (d_sums2) return launch_tables(c, w, batch, s, true, true, bl, beta_app, hard ? 1 : 0, d_sums2, nullptr, app == 0);
+    if (d_sums2) return launch_tables(c, w, batch, s, true, true, bl, beta_app, hard ? 1 : 0, d_sums2, nullptr, app == 0, hp);
     return launch_tables(c, w, batch, s, true, app != 0, bl, beta_app, hard ? 1 : 0, nullptr, nullptr);
 }
 
@@ -726,9 +727,9 @@ namespace pdwt {
 int norm_finish(pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, const double* d_sums, double* h_sums);
 // thresholds of the Wavelets object: d_sums2 receives the norms of the result (see threshold_impl)
 int threshold_norms(float** c, float beta, pdwt_w_info w, int app, int normalize, int batch, cudaStream_t s, int hard,
-                    double* d_sums2)
+                    double* d_sums2, const HostPublish* hp)
 {
-    return threshold_impl(c, beta, w, app, normalize, batch, s, hard, d_sums2);
+    return threshold_impl(c, beta, w, app, normalize, batch, s, hard, d_sums2, hp);
 }
 // shared with the Wavelets object: reduction with caller-provided scratch (d_sums/h_sums: batch*kMaxSeg doubles)
 int norm_impl(float** c, pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, double* d_sums, double* h_sums)
@@ -742,13 +743,11 @@ int norm_impl(float** c, pdwt_w_info w, int batch, int mode, float* out, cudaStr
     return norm_finish(w, batch, mode, out, s, d_sums, h_sums);
 }
 
-// the sums are on the device (one double per plane and sub-band, details first, A last): fetch them and accumulate in
-// float, sub-band by sub-band in the reference's order (wt.cu:373-394, 400-417)
-int norm_finish(pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, const double* d_sums, double* h_sums)
+// one double per plane and sub-band (details first, A last) -> the reference's float accumulation, sub-band by sub-band
+// in its order (wt.cu:373-394, 400-417)
+void norm_accumulate(pdwt_w_info w, int batch, int mode, float* out, const double* h_sums)
 {
     const int nseg = pdwt_num_coeffs(w);
-    PDWT_CUDA(cudaMemcpyAsync(h_sums, d_sums, sizeof(double) * batch * nseg, cudaMemcpyDeviceToHost, s));
-    PDWT_CUDA(cudaStreamSynchronize(s));
     for (int p = 0; p < batch; p++) {
         float res = 0.0f;
         for (int k = 0; k < nseg; k++) {
@@ -762,6 +761,63 @@ int norm_finish(pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, 
         }
         out[p] = res;
     }
+}
+
+// the sums are on the device: fetch them, then accumulate
+int norm_finish(pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, const double* d_sums, double* h_sums)
+{
+    const int nseg = pdwt_num_coeffs(w);
+    PDWT_CUDA(cudaMemcpyAsync(h_sums, d_sums, sizeof(double) * batch * nseg, cudaMemcpyDeviceToHost, s));
+    PDWT_CUDA(cudaStreamSynchronize(s));
+    norm_accumulate(w, batch, mode, out, h_sums);
+    return PDWT_OK;
+}
+
+// ---- HostPublish, host side ----------------------------------------------------------------------------------
+unsigned next_publish_tag()
+{
+    static unsigned tag = 0;   // process-wide; 0 is what fresh buffers hold
+    unsigned t;
+    do t = __atomic_add_fetch(&tag, 1u, __ATOMIC_RELAXED); while (t == 0);
+    return t;
+}
+// Spin until the launch that carries `tag` has published its nsums doubles into the pinned words h; they are decoded
+// into vals.  Every 1024 probes the stream is queried: if it has drained (or failed) and the words are still not there,
+// the caller gets an error instead of a hang.
+int wait_published(const unsigned long long* h, int nsums, unsigned tag, double* vals, cudaStream_t s)
+{
+    const volatile unsigned long long* w = h;
+    unsigned spins = 0;
+    bool drained = false;
+    for (int i = 0; i < nsums; i++) {
+        unsigned long long a, b;
+        for (;;) {
+            a = w[2 * i];
+            b = w[2 * i + 1];
+            if ((unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag) break;
+            if (drained) return PDWT_ERR_CUDA;   // the stream is idle and nothing arrived
+            if ((++spins & 1023u) == 0) {
+                const cudaError_t e = cudaStreamQuery(s);
+                if (e == cudaErrorNotReady) continue;
+                if (e != cudaSuccess) return note_cuda(e);
+                drained = true;   // one more look at the words, then give up
+            }
+        }
+        const unsigned long long bits = (a & 0xffffffffull) | (b << 32);
+        memcpy(&vals[i], &bits, sizeof bits);
+    }
+    return PDWT_OK;
+}
+// norm of the coefficients with the result delivered through hp (d_sums zero on entry and on exit)
+int norm_published(float** c, pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, double* d_sums,
+                   const HostPublish& hp, const unsigned long long* h_words, double* vals)
+{
+    if (!c || !out || w.nlevels < 1 || batch < 1) return PDWT_ERR_ARG;
+    if (pdwt_num_coeffs(w) > kMaxSeg) return PDWT_ERR_ARG;
+    int pushed = 0;
+    TRY(launch_tables(c, w, batch, s, true, true, nullptr, 0.f, 2 + mode, d_sums, &pushed, false, &hp));
+    TRY(wait_published(h_words, hp.nsums, hp.tag, vals, s));
+    norm_accumulate(w, batch, mode, out, vals);
     return PDWT_OK;
 }
 }  // namespace pdwt

@@ -197,10 +197,21 @@ struct SegTable {  // list of (sub-band, length, parameter) handled by one launc
     float beta[kMaxSeg];
     unsigned char ro[kMaxSeg];           // 1: the element-wise kernels only READ this segment (it is there for its norm)
 };
+// Hand-over of the sums to the host without a memset in front of the launch, a copy behind it or a system-scope fence
+// inside it: the LAST block to finish (device ticket) writes every double into mapped pinned memory as two 8-byte words
+// {32 data bits, 32-bit tag of this launch} -- an aligned 8-byte store is the unit that reaches host memory whole (the
+// scheme of NCCL's LL protocol) -- and leaves the device scratch and the ticket zeroed for the next launch.  The host
+// spins until both words of every sum carry the tag (wait_published) instead of cudaMemcpyAsync + cudaStreamSynchronize.
+struct HostPublish {
+    unsigned long long* h_out;   // device view of the pinned words: 2 per sum
+    unsigned* ticket;            // zero between launches
+    unsigned tag;                // announces THIS launch's sums (never 0)
+    int nsums;
+};
 // sums != NULL: the kernel also accumulates sum |out| into sums[plane*nseg + seg] and sum out^2 into
 // sums[batch*nseg + plane*nseg + seg] (the norm of the thresholded coefficients comes for free)
 int e_threshold(const SegTable& tab, int op /*0 soft, 1 hard, 2 proj_linf, 3 scale by beta*/, int batch, cudaStream_t s,
-                double* sums = nullptr);
+                double* sums = nullptr, const HostPublish* hp = nullptr);
 struct GroupTable {  // group soft threshold: per level the detail triple (h, v NULL in 1-D) and, optionally, A
     int nlev;
     float *h[32], *v[32], *d[32], *a[32];
@@ -217,7 +228,7 @@ struct PairTable {  // dst += alpha * src, sub-band by sub-band
 int e_axpy(const PairTable& tab, float alpha, int batch, cudaStream_t s);
 int e_circshift(const float* in, float* out, size_t stride, int Nr, int Nc, int sr, int sc, int batch, cudaStream_t s);
 // sums[plane*nseg + seg] (double, device) += sum |v| (mode 0) or sum v^2 (mode 1)
-int e_reduce(const SegTable& tab, int mode, int batch, double* d_sums, cudaStream_t s);
+int e_reduce(const SegTable& tab, int mode, int batch, double* d_sums, cudaStream_t s, const HostPublish* hp = nullptr);
 
 }  // namespace pdwt
 

@@ -1,9 +1,10 @@
 // pdwt_elementwise.cu -- soft / hard threshold and L1 / L2 reductions over a table of sub-bands.
 //
 // The reference launches one 16x16-block kernel per level (common.cu:219-282) and, for the norms, one blocking
-// cuBLAS call per sub-band (wt.cu:370-418).  Here ONE launch covers every sub-band of every plane: grid.y walks
-// the segment table, grid.z the planes, and each thread streams 128-bit vectors (scalar head/tail for unaligned
-// planes).  Pure HBM streaming: 8 B/coefficient for a threshold, 4 B/coefficient for a norm.
+// cuBLAS call per sub-band (wt.cu:370-418).  Here ONE launch covers every sub-band of every plane: a persistent grid
+// walks the segment table as one flat list of 32 KB tiles (see walk_tiles), each thread streaming 8 independent
+// 128-bit vectors per tile (scalar head/tail for unaligned planes).  Pure HBM streaming: 8 B/coefficient for a
+// threshold, 4 B/coefficient for a norm.
 #include "pdwt_common.cuh"
 
 namespace pdwt {
@@ -26,25 +27,132 @@ __device__ __forceinline__ float ew1(float v, float beta)
     return OP == 0 ? soft1(v, beta) : OP == 1 ? hard1(v, beta) : OP == 2 ? linf1(v, beta) : __fmul_rn(beta, v);
 }
 
-template <int OP, bool SUMS>
-__global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTable tab, double* __restrict__ sums, int batch)
+// ---- flat persistent walk over (plane, segment) -----------------------------------------------------------------
+// The sub-bands of a transform differ in size by 4^level, so a grid with one axis per segment ends up with many short
+// blocks (two dependent rounds of loads each) and the HBM pipe never fills (ncu: 3.2 TB/s).  Instead the whole table is
+// ONE list of tiles -- kTileV 128-bit vectors, 8 per thread -- laid out plane by plane, segment by segment; block b of
+// the (at most 4 x SMs) resident blocks walks the CONTIGUOUS tile range [b*T/nb, (b+1)*T/nb) with 8 independent
+// 128-bit loads in flight per thread and flushes its partial sums (block reduction, one double atomic) only where
+// its range crosses into another sub-band: a handful of atomics per block.
+constexpr int kEwThreads = 256;
+constexpr int kVecPerThread = 8;
+constexpr int kTileV = kEwThreads * kVecPerThread;   // 128-bit vectors per tile (32 KB)
+
+__host__ __device__ inline unsigned long long seg_tiles(unsigned long long n)
 {
-    const int seg = blockIdx.y;
-    float* p = tab.ptr[seg] + (size_t)blockIdx.z * tab.stride[seg];
-    const size_t n = tab.n[seg];
-    const float beta = tab.beta[seg];
-    // scalar head up to the first 16-byte boundary, vector body, scalar tail
-    size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;
-    if (head > n) head = n;
-    const size_t nvec = (n - head) >> 2;
-    // the grid is sized for the largest segment: a smaller one uses only as many blocks as give a thread >= 4 vectors
-    const size_t nb = min((size_t)gridDim.x, (nvec + 1023) / 1024 + 1);
-    if (blockIdx.x >= nb) return;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = nb * blockDim.x;
-    float4* pv = reinterpret_cast<float4*>(p + head);
-    const bool ro = tab.ro[seg] != 0;   // read-only segment: only its sums are wanted
-    double s1 = 0.0, s2 = 0.0;          // sum |out|, sum out^2 (SUMS); per vector in float like k_reduce, then double
-    auto apply = [&](float4 v) {
+    const unsigned long long nv = n >> 2;   // upper bound of the aligned vectors in the body
+    return nv <= (unsigned long long)kTileV ? 1ull : (nv + kTileV - 1) / kTileV;   // >= 1: tile 0 owns head and tail
+}
+
+struct SegCursor {   // where a block stands in the tile list
+    const float* p;  // first float of the (plane, segment)
+    size_t n, head, nvec;
+    unsigned long long lt, lt_end;   // local tile range of this block inside the segment
+    int seg, plane;
+};
+
+// block-wide sum of one double per thread; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* scratch /*[8]*/)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        v = lane < kEwThreads / 32 ? scratch[lane] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    __syncthreads();   // scratch may be reused right away
+    return v;
+}
+
+// see HostPublish (pdwt_common.cuh).  Every thread of every block calls it once, after its last atomic on `sums`.
+__device__ __forceinline__ void publish_sums(const HostPublish& hp, double* sums)
+{
+    if (!hp.h_out) return;
+    __shared__ unsigned is_last;
+    if (threadIdx.x == 0) {
+        __threadfence();   // this block's atomics are performed before its ticket
+        is_last = atomicAdd(hp.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const unsigned long long tag = (unsigned long long)hp.tag << 32;
+    for (int i = threadIdx.x; i < hp.nsums; i += blockDim.x) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(__ldcg(sums + i));   // the atomics live in L2
+        sums[i] = 0.0;
+        asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(hp.h_out + 2 * i), "l"(tag | (b & 0xffffffffull)),
+                     "l"(tag | (b >> 32))
+                     : "memory");
+    }
+    if (threadIdx.x == 0) *hp.ticket = 0;   // every block has drawn its ticket: nobody touches it before the next launch
+}
+
+// Drives `tile(cursor, first vector index of the tile, full)`, `edge(cursor, index)` for the scalar head / tail elements
+// and `flush(cursor)` at the end of every (plane, segment) piece of the block's range.  All control flow is block-uniform.
+template <class TileFn, class EdgeFn, class FlushFn>
+__device__ __forceinline__ void walk_tiles(const SegTable& tab, int batch, unsigned long long* pre /*shared [kMaxSeg+1]*/,
+                                           TileFn tile, EdgeFn edge, FlushFn flush)
+{
+    if (threadIdx.x == 0) {
+        unsigned long long a = 0;
+        for (int s = 0; s < tab.nseg; s++) {
+            pre[s] = a;
+            a += seg_tiles(tab.n[s]);
+        }
+        pre[tab.nseg] = a;
+    }
+    __syncthreads();
+    const unsigned long long TP = pre[tab.nseg], total = TP * (unsigned long long)batch;
+    unsigned long long t = total * blockIdx.x / gridDim.x;
+    const unsigned long long t1 = total * (blockIdx.x + 1ull) / gridDim.x;
+    if (t >= t1) return;
+    SegCursor c;
+    c.plane = (int)(t / TP);
+    const unsigned long long r = t - (unsigned long long)c.plane * TP;
+    c.seg = 0;
+    while (pre[c.seg + 1] <= r) c.seg++;
+    c.lt = r - pre[c.seg];
+    for (;;) {
+        c.p = tab.ptr[c.seg] + (size_t)c.plane * tab.stride[c.seg];
+        c.n = tab.n[c.seg];
+        c.head = ((16 - ((uintptr_t)c.p & 15)) & 15) >> 2;   // scalar head up to the first 16-byte boundary
+        if (c.head > c.n) c.head = c.n;
+        c.nvec = (c.n - c.head) >> 2;
+        const unsigned long long ntile = pre[c.seg + 1] - pre[c.seg];
+        c.lt_end = min(ntile, c.lt + (t1 - t));
+        t += c.lt_end - c.lt;
+        if (c.lt == 0) {   // tile 0 also owns the scalar head and tail (at most 3 + 3 elements)
+            const size_t tail0 = c.head + (c.nvec << 2);
+            if (threadIdx.x < c.head) edge(c, (size_t)threadIdx.x);
+            else if (threadIdx.x >= 32 && tail0 + (threadIdx.x - 32) < c.n) edge(c, tail0 + (threadIdx.x - 32));
+        }
+        for (unsigned long long lt = c.lt; lt < c.lt_end; lt++) {
+            const size_t v0 = (size_t)lt * kTileV;
+            if (v0 >= c.nvec) break;
+            tile(c, v0, v0 + kTileV <= c.nvec);
+        }
+        flush(c);
+        if (t >= t1) return;
+        c.lt = 0;
+        if (++c.seg == tab.nseg) {
+            c.seg = 0;
+            c.plane++;
+        }
+    }
+}
+
+template <int OP, bool SUMS>
+__global__ void __launch_bounds__(kEwThreads, SUMS ? 3 : 4)
+    k_threshold(const __grid_constant__ SegTable tab, double* sums, int batch, const HostPublish hp)
+{
+    __shared__ unsigned long long pre[kMaxSeg + 1];
+    __shared__ double scratch[kEwThreads / 32];
+    double s1 = 0.0, s2 = 0.0;   // sum |out|, sum out^2 (SUMS); per vector in float like k_reduce, then double
+    auto apply = [&](float4 v, const float beta, const bool ro) {
         if (!ro) {
             v.x = ew1<OP>(v.x, beta); v.y = ew1<OP>(v.y, beta); v.z = ew1<OP>(v.z, beta); v.w = ew1<OP>(v.w, beta);
         }
@@ -54,144 +162,132 @@ __global__ void __launch_bounds__(256) k_threshold(const __grid_constant__ SegTa
         }
         return v;
     };
-    auto apply1 = [&](float v) {
-        if (!ro) v = ew1<OP>(v, beta);
-        if (SUMS) {
-            s1 += (double)fabsf(v);
-            s2 += (double)(v * v);
-        }
-        return v;
-    };
-    size_t i = tid;
-    for (; i + 3 * nth < nvec; i += 4 * nth) {   // four independent 128-bit loads in flight per thread
-        const float4 a = apply(pv[i]), b = apply(pv[i + nth]), c = apply(pv[i + 2 * nth]), d = apply(pv[i + 3 * nth]);
-        if (!ro) {
-            pv[i] = a;
-            pv[i + nth] = b;
-            pv[i + 2 * nth] = c;
-            pv[i + 3 * nth] = d;
-        }
-    }
-    for (; i < nvec; i += nth) {
-        const float4 a = apply(pv[i]);
-        if (!ro) pv[i] = a;
-    }
-    if (tid < head) {
-        const float a = apply1(p[tid]);
-        if (!ro) p[tid] = a;
-    }
-    const size_t tail0 = head + (nvec << 2);
-    if (tail0 + tid < n) {
-        const float a = apply1(p[tail0 + tid]);
-        if (!ro) p[tail0 + tid] = a;
-    }
-    if (SUMS) {
+    walk_tiles(
+        tab, batch, pre,
+        [&](const SegCursor& c, const size_t v0, const bool full) {
+            const float beta = tab.beta[c.seg];
+            const bool ro = tab.ro[c.seg] != 0;   // read-only segment: only its sums are wanted
+            float4* pv = reinterpret_cast<float4*>(const_cast<float*>(c.p) + c.head) + v0 + threadIdx.x;
+            float4 v[kVecPerThread];
+            if (full) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        }
-        __shared__ double w1[8], w2[8];
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        if (lane == 0) {
-            w1[wid] = s1;
-            w2[wid] = s2;
-        }
-        __syncthreads();
-        if (wid == 0) {
-            s1 = lane < 8 ? w1[lane] : 0.0;
-            s2 = lane < 8 ? w2[lane] : 0.0;
+                for (int k = 0; k < kVecPerThread; k++) v[k] = pv[k * kEwThreads];   // 8 independent 128-bit loads
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                for (int k = 0; k < kVecPerThread; k++) v[k] = apply(v[k], beta, ro);
+                if (!ro) {
+#pragma unroll
+                    for (int k = 0; k < kVecPerThread; k++) pv[k * kEwThreads] = v[k];
+                }
+            } else {
+                const size_t left = c.nvec - v0;   // vectors in this (last) tile
+#pragma unroll
+                for (int k = 0; k < kVecPerThread; k++)
+                    if (threadIdx.x + (size_t)k * kEwThreads < left) v[k] = pv[k * kEwThreads];
+#pragma unroll
+                for (int k = 0; k < kVecPerThread; k++)
+                    if (threadIdx.x + (size_t)k * kEwThreads < left) {
+                        v[k] = apply(v[k], beta, ro);
+                        if (!ro) pv[k * kEwThreads] = v[k];
+                    }
             }
-            if (lane == 0) {
-                const size_t k = (size_t)blockIdx.z * tab.nseg + seg;
-                atomicAdd(&sums[k], s1);
-                atomicAdd(&sums[(size_t)batch * tab.nseg + k], s2);
+        },
+        [&](const SegCursor& c, const size_t i) {
+            float* q = const_cast<float*>(c.p) + i;
+            float v = *q;
+            if (!tab.ro[c.seg]) {
+                v = ew1<OP>(v, tab.beta[c.seg]);
+                *q = v;
             }
-        }
-    }
+            if (SUMS) {
+                s1 += (double)fabsf(v);
+                s2 += (double)(v * v);
+            }
+        },
+        [&](const SegCursor& c) {
+            if (SUMS) {
+                const double a = block_sum(s1, scratch), b = block_sum(s2, scratch);
+                if (threadIdx.x == 0) {
+                    const size_t k = (size_t)c.plane * tab.nseg + c.seg;
+                    atomicAdd(&sums[k], a);
+                    atomicAdd(&sums[(size_t)batch * tab.nseg + k], b);
+                }
+                s1 = s2 = 0.0;
+            }
+        });
+    if (SUMS) publish_sums(hp, sums);
 }
 
-// sum |v| (MODE 0) or sum v^2 (MODE 1): per-thread double accumulation of float4 loads, warp shuffle tree,
-// one shared-memory pass across the 8 warps, one double atomicAdd per block.
-// (256, 4): without the bound ptxas took 96 registers, two blocks per SM, and the loads' latency showed (ncu: 8 cycles of
-// long_scoreboard per issue, 2.7 TB/s)
+// sum |v| (MODE 0) or sum v^2 (MODE 1): the four terms of one vector are added in float (exact enough: 4 terms), the
+// running sum in double; warp shuffle tree, one shared-memory pass across the 8 warps, one double atomicAdd per
+// (block, sub-band) piece.
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) k_reduce(const __grid_constant__ SegTable tab, double* __restrict__ sums)
+__global__ void __launch_bounds__(kEwThreads, 4)
+    k_reduce(const __grid_constant__ SegTable tab, double* sums, int batch, const HostPublish hp)
 {
-    const int seg = blockIdx.y;
-    const float* p = tab.ptr[seg] + (size_t)blockIdx.z * tab.stride[seg];
-    const size_t n = tab.n[seg];
-    size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;
-    if (head > n) head = n;
-    const size_t nvec = (n - head) >> 2;
-    const size_t nb = min((size_t)gridDim.x, (nvec + 1023) / 1024 + 1);   // blocks that take part in this segment
-    if (blockIdx.x >= nb) return;                                        // (no atomic from the others)
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = nb * blockDim.x;
-    const float4* pv = reinterpret_cast<const float4*>(p + head);
+    __shared__ unsigned long long pre[kMaxSeg + 1];
+    __shared__ double scratch[kEwThreads / 32];
     double acc = 0.0;
     auto term = [](float v) -> float { return MODE ? v * v : fabsf(v); };
-    // the four terms of one vector are added in float (exact enough: 4 terms), the running sum in double
     auto vsum = [&](const float4 v) -> double { return (double)((term(v.x) + term(v.y)) + (term(v.z) + term(v.w))); };
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (size_t i = tid; i < nvec; i += 4 * nth) {   // four independent (guarded) 128-bit loads in flight per thread
-        const float4 a = __ldg(pv + i);
-        const float4 b = i + nth < nvec ? __ldg(pv + i + nth) : z4;
-        const float4 c = i + 2 * nth < nvec ? __ldg(pv + i + 2 * nth) : z4;
-        const float4 d = i + 3 * nth < nvec ? __ldg(pv + i + 3 * nth) : z4;
-        acc += (vsum(a) + vsum(b)) + (vsum(c) + vsum(d));
-    }
-    if (tid < head) acc += (double)term(p[tid]);
-    const size_t tail0 = head + (nvec << 2);
-    if (tail0 + tid < n) acc += (double)term(p[tail0 + tid]);
-
+    walk_tiles(
+        tab, batch, pre,
+        [&](const SegCursor& c, const size_t v0, const bool full) {
+            const float4* pv = reinterpret_cast<const float4*>(c.p + c.head) + v0 + threadIdx.x;
+            float4 v[kVecPerThread];
+            const size_t left = c.nvec - v0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    __shared__ double warp_sum[8];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) warp_sum[wid] = acc;
-    __syncthreads();
-    if (wid == 0) {
-        acc = lane < 8 ? warp_sum[lane] : 0.0;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) atomicAdd(&sums[(size_t)blockIdx.z * tab.nseg + seg], acc);
-    }
+            for (int k = 0; k < kVecPerThread; k++)   // 8 independent 128-bit loads in flight per thread
+                v[k] = (full || threadIdx.x + (size_t)k * kEwThreads < left) ? __ldg(pv + k * kEwThreads)
+                                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc += ((vsum(v[0]) + vsum(v[1])) + (vsum(v[2]) + vsum(v[3]))) +
+                   ((vsum(v[4]) + vsum(v[5])) + (vsum(v[6]) + vsum(v[7])));
+        },
+        [&](const SegCursor& c, const size_t i) { acc += (double)term(c.p[i]); },
+        [&](const SegCursor& c) {
+            const double a = block_sum(acc, scratch);
+            if (threadIdx.x == 0) atomicAdd(&sums[(size_t)c.plane * tab.nseg + c.seg], a);
+            acc = 0.0;
+        });
+    publish_sums(hp, sums);
 }
 
-static int blocks_for(const SegTable& tab, int per_sm = 4)
+// resident blocks that walk the tile list: up to per_sm per SM, never more than there are tiles
+static int blocks_for(const SegTable& tab, int batch, int per_sm)
 {
-    unsigned long long nmax = 0;
-    for (int i = 0; i < tab.nseg; i++) nmax = tab.n[i] > nmax ? tab.n[i] : nmax;
-    // 256 threads x 4 floats x 4 vectors in flight per thread per pass; at most 4 blocks per SM per segment (the segment
-    // table puts nseg of these grids side by side)
-    unsigned long long b = (nmax + 4095) / 4096;
+    unsigned long long tiles = 0;
+    for (int i = 0; i < tab.nseg; i++) tiles += seg_tiles(tab.n[i]);
+    tiles *= (unsigned long long)batch;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) {
+        cudaGetLastError();
+        sms = 148;
+    }
+    unsigned long long b = (unsigned long long)sms * per_sm;
+    if (b > tiles) b = tiles;
     if (b < 1) b = 1;
-    if (b > 148ull * per_sm) b = 148ull * per_sm;
     return (int)b;
 }
 
-int e_threshold(const SegTable& tab, int op, int batch, cudaStream_t s, double* sums)
+int e_threshold(const SegTable& tab, int op, int batch, cudaStream_t s, double* sums, const HostPublish* hpp)
 {
+    const HostPublish hp = hpp ? *hpp : HostPublish{nullptr, nullptr, 0, 0};
     PDWT_PROF(__func__, s);
     if (tab.nseg == 0) return 0;
-    dim3 grid(blocks_for(tab, sums ? 2 : 4), tab.nseg, batch);
+    const int th = kEwThreads;
+    dim3 grid(blocks_for(tab, batch, sums ? 3 : 4));
     if (sums) {   // thresholds that also deliver the norms of their result
         switch (op) {
-            case 0: k_threshold<0, true><<<grid, 256, 0, s>>>(tab, sums, batch); break;
-            case 1: k_threshold<1, true><<<grid, 256, 0, s>>>(tab, sums, batch); break;
-            case 2: k_threshold<2, true><<<grid, 256, 0, s>>>(tab, sums, batch); break;
-            default: k_threshold<3, true><<<grid, 256, 0, s>>>(tab, sums, batch); break;
+            case 0: k_threshold<0, true><<<grid, th, 0, s>>>(tab, sums, batch, hp); break;
+            case 1: k_threshold<1, true><<<grid, th, 0, s>>>(tab, sums, batch, hp); break;
+            case 2: k_threshold<2, true><<<grid, th, 0, s>>>(tab, sums, batch, hp); break;
+            default: k_threshold<3, true><<<grid, th, 0, s>>>(tab, sums, batch, hp); break;
         }
     } else {
         switch (op) {
-            case 0: k_threshold<0, false><<<grid, 256, 0, s>>>(tab, nullptr, batch); break;
-            case 1: k_threshold<1, false><<<grid, 256, 0, s>>>(tab, nullptr, batch); break;
-            case 2: k_threshold<2, false><<<grid, 256, 0, s>>>(tab, nullptr, batch); break;
-            default: k_threshold<3, false><<<grid, 256, 0, s>>>(tab, nullptr, batch); break;
+            case 0: k_threshold<0, false><<<grid, th, 0, s>>>(tab, nullptr, batch, hp); break;
+            case 1: k_threshold<1, false><<<grid, th, 0, s>>>(tab, nullptr, batch, hp); break;
+            case 2: k_threshold<2, false><<<grid, th, 0, s>>>(tab, nullptr, batch, hp); break;
+            default: k_threshold<3, false><<<grid, th, 0, s>>>(tab, nullptr, batch, hp); break;
         }
     }
     PDWT_LAUNCH_CHECK();
@@ -295,15 +391,16 @@ int e_circshift(const float* in, float* out, size_t stride, int Nr, int Nc, int 
     return 0;
 }
 
-int e_reduce(const SegTable& tab, int mode, int batch, double* d_sums, cudaStream_t s)
+int e_reduce(const SegTable& tab, int mode, int batch, double* d_sums, cudaStream_t s, const HostPublish* hpp)
 {
+    const HostPublish hp = hpp ? *hpp : HostPublish{nullptr, nullptr, 0, 0};
     PDWT_PROF(__func__, s);
     if (tab.nseg == 0) return 0;
-    dim3 grid(blocks_for(tab, 4), tab.nseg, batch);   // one double atomic per block: keep them few
+    dim3 grid(blocks_for(tab, batch, 4));
     if (mode)
-        k_reduce<1><<<grid, 256, 0, s>>>(tab, d_sums);
+        k_reduce<1><<<grid, kEwThreads, 0, s>>>(tab, d_sums, batch, hp);
     else
-        k_reduce<0><<<grid, 256, 0, s>>>(tab, d_sums);
+        k_reduce<0><<<grid, kEwThreads, 0, s>>>(tab, d_sums, batch, hp);
     PDWT_LAUNCH_CHECK();
     return 0;
 }

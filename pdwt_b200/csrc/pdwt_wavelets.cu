@@ -15,7 +15,12 @@ namespace pdwt {
 int norm_impl(float** c, pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, double* d_sums, double* h_sums);
 int norm_finish(pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, const double* d_sums, double* h_sums);
 int threshold_norms(float** c, float beta, pdwt_w_info w, int app, int normalize, int batch, cudaStream_t s, int hard,
-                    double* d_sums2);
+                    double* d_sums2, const HostPublish* hp);
+void norm_accumulate(pdwt_w_info w, int batch, int mode, float* out, const double* h_sums);
+unsigned next_publish_tag();
+int wait_published(const unsigned long long* h, int nsums, unsigned tag, double* vals, cudaStream_t s);
+int norm_published(float** c, pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, double* d_sums,
+                   const HostPublish& hp, const unsigned long long* h_words, double* vals);
 }
 using namespace pdwt;
 
@@ -41,7 +46,7 @@ static bool norm_cache_enabled()
 Wavelets::Wavelets()
     : d_image(NULL), d_coeffs(NULL), d_tmp(NULL), current_shift_r(0), current_shift_c(0), do_separable(1),
       do_cycle_spinning(0), state(W_INIT), batch(1), last_error(0), stream(NULL), async_copies(0), filters(NULL),
-      d_sums(NULL), h_sums(NULL), launches(0), norm_cache(0)
+      d_sums(NULL), h_sums(NULL), launches(0), norm_cache(0), h_sums_dev(NULL), thr_tag(0)
 {
     memset(wname, 0, sizeof wname);
     memset(&winfos, 0, sizeof winfos);
@@ -53,8 +58,18 @@ int Wavelets::alloc_buffers()
     int rc;
     if ((rc = cuda_rc(cudaMalloc(&d_image, sizeof(DTYPE) * plane * batch))) < 0) return rc;
     if ((rc = cuda_rc(cudaMalloc(&d_tmp, sizeof(DTYPE) * 2 * plane * batch))) < 0) return rc;  // wt.cu:128-130
-    if ((rc = cuda_rc(cudaMalloc(&d_sums, sizeof(double) * 3 * kMaxSeg * batch))) < 0) return rc;
-    if ((rc = cuda_rc(cudaMallocHost(&h_sums, sizeof(double) * kMaxSeg * batch))) < 0) return rc;
+    // Norm scratch (HostPublish, pdwt_common.cuh).  With cap = kMaxSeg * batch:
+    //   device (doubles): [0, cap) reduction sums | [cap, 3 cap) L1 and L2 sums left by a threshold | two tickets; all
+    //           zero between launches
+    //   host (pinned, mapped; 8-byte words): [0, 2 cap) published reduction sums | [2 cap, 6 cap) published threshold
+    //           sums | [6 cap, 8 cap) the decoded doubles (host only)
+    const size_t cap = (size_t)kMaxSeg * batch;
+    if ((rc = cuda_rc(cudaMalloc(&d_sums, sizeof(double) * (3 * cap + 2)))) < 0) return rc;
+    if ((rc = cuda_rc(cudaMemset(d_sums, 0, sizeof(double) * (3 * cap + 2)))) < 0) return rc;
+    if ((rc = cuda_rc(cudaDeviceSynchronize())) < 0) return rc;   // once per object: the zeros precede any stream's work
+    if ((rc = cuda_rc(cudaHostAlloc(&h_sums, sizeof(double) * 8 * cap, cudaHostAllocMapped))) < 0) return rc;
+    memset(h_sums, 0, sizeof(double) * 8 * cap);
+    if ((rc = cuda_rc(cudaHostGetDevicePointer(&h_sums_dev, h_sums, 0))) < 0) return rc;
     return PDWT_OK;
 }
 
@@ -74,7 +89,7 @@ void Wavelets::free_buffers()
     if (filters) pdwt_filters_destroy(filters);
     d_image = d_tmp = NULL;
     d_coeffs = NULL;
-    d_sums = h_sums = NULL;
+    d_sums = h_sums = h_sums_dev = NULL;
     filters = NULL;
 }
 
@@ -83,7 +98,7 @@ Wavelets::Wavelets(DTYPE* img, int Nr, int Nc, const char* name, int levels, int
                    int do_cycle_spinning_, int do_swt, int ndim, int batch_)
     : d_image(NULL), d_coeffs(NULL), d_tmp(NULL), current_shift_r(0), current_shift_c(0), do_separable(do_separable_),
       do_cycle_spinning(do_cycle_spinning_), state(W_INIT), batch(batch_ < 1 ? 1 : batch_), last_error(0), stream(NULL),
-      async_copies(0), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0), norm_cache(0)
+      async_copies(0), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0), norm_cache(0), h_sums_dev(NULL), thr_tag(0)
 {
     memset(wname, 0, sizeof wname);
     winfos.Nr = Nr;
@@ -183,7 +198,7 @@ Wavelets::Wavelets(DTYPE* img, int Nr, int Nc, const char* name, int levels, int
 Wavelets::Wavelets(const Wavelets& W)
     : d_image(NULL), d_coeffs(NULL), d_tmp(NULL), current_shift_r(W.current_shift_r), current_shift_c(W.current_shift_c),
       do_separable(W.do_separable), do_cycle_spinning(W.do_cycle_spinning), winfos(W.winfos), state(W.state),
-      batch(W.batch), last_error(0), stream(W.stream), async_copies(W.async_copies), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0), norm_cache(0)
+      batch(W.batch), last_error(0), stream(W.stream), async_copies(W.async_copies), filters(NULL), d_sums(NULL), h_sums(NULL), launches(0), norm_cache(0), h_sums_dev(NULL), thr_tag(0)
 {
     memcpy(wname, W.wname, sizeof wname);
     if (winfos.Nr < 1 || winfos.Nc < 1) return;
@@ -272,9 +287,12 @@ void Wavelets::soft_threshold(DTYPE beta, int do_thresh_appcoeffs, int normalize
     // the same launch leaves the L1 / L2 norms of the thresholded coefficients in d_sums (second and third block): a
     // norm1() / norm2sq() that follows needs no pass over the coefficients
     norm_cache = 0;
+    HostPublish hp;
+    publish_target(1, &hp);
     W_TRY(threshold_norms(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, (cudaStream_t)stream, 0,
-                          d_sums + (size_t)kMaxSeg * batch),
+                          d_sums + (size_t)kMaxSeg * batch, &hp),
           W_THRESHOLD_ERROR);
+    thr_tag = hp.tag;
     norm_cache = (pdwt_num_coeffs(winfos) <= kMaxSeg && norm_cache_enabled()) ? 3 : 0;
     launches += pdwt_launch_count() - before;
 }
@@ -289,9 +307,12 @@ void Wavelets::hard_threshold(DTYPE beta, int do_thresh_appcoeffs, int normalize
     if (state == W_CREATION_ERROR) return;
     const long long before = pdwt_launch_count();
     norm_cache = 0;
+    HostPublish hp;
+    publish_target(1, &hp);
     W_TRY(threshold_norms(d_coeffs, beta, winfos, do_thresh_appcoeffs, normalize, batch, (cudaStream_t)stream, 1,
-                          d_sums + (size_t)kMaxSeg * batch),
+                          d_sums + (size_t)kMaxSeg * batch, &hp),
           W_THRESHOLD_ERROR);
+    thr_tag = hp.tag;
     norm_cache = (pdwt_num_coeffs(winfos) <= kMaxSeg && norm_cache_enabled()) ? 3 : 0;
     launches += pdwt_launch_count() - before;
 }
@@ -387,16 +408,35 @@ int Wavelets::add_wavelet_ref(const Wavelets& W, DTYPE alpha)
     return 0;
 }
 
+// where launch `which` (0: a reduction, 1: a threshold that leaves its norms) delivers its sums, see alloc_buffers()
+void Wavelets::publish_target(int which, HostPublish* out) const
+{
+    const size_t cap = (size_t)kMaxSeg * batch;
+    const int nseg = pdwt_num_coeffs(winfos);
+    HostPublish& hp = *out;
+    hp.h_out = reinterpret_cast<unsigned long long*>(h_sums_dev) + (which ? 2 * cap : 0);
+    hp.ticket = reinterpret_cast<unsigned*>(d_sums + 3 * cap) + which;
+    hp.tag = next_publish_tag();
+    hp.nsums = (which ? 2 : 1) * batch * nseg;
+}
+
 int Wavelets::norms(int mode, DTYPE* out)
 {
     if (state == W_CREATION_ERROR || !d_coeffs) return PDWT_ERR_STATE;
     const long long before = pdwt_launch_count();
     int rc;
-    if (norm_cache & (1 << mode))   // left behind by the last threshold: [kMaxSeg*batch + mode*batch*ncoeffs ...]
-        rc = norm_finish(winfos, batch, mode, out, (cudaStream_t)stream,
-                         d_sums + (size_t)kMaxSeg * batch + (size_t)mode * batch * pdwt_num_coeffs(winfos), h_sums);
-    else
-        rc = norm_impl(d_coeffs, winfos, batch, mode, out, (cudaStream_t)stream, d_sums, h_sums);
+    const size_t cap = (size_t)kMaxSeg * batch;
+    const unsigned long long* words = reinterpret_cast<const unsigned long long*>(h_sums);
+    double* vals = h_sums + 6 * cap;
+    const int n1 = batch * pdwt_num_coeffs(winfos);
+    if (norm_cache & (1 << mode)) {   // published by the last threshold: L1 sums, then L2 sums (batch * ncoeffs each)
+        rc = wait_published(words + 2 * cap, 2 * n1, thr_tag, vals, (cudaStream_t)stream);
+        if (rc == PDWT_OK) norm_accumulate(winfos, batch, mode, out, vals + (size_t)mode * n1);
+    } else {
+        HostPublish hp;
+        publish_target(0, &hp);
+        rc = norm_published(d_coeffs, winfos, batch, mode, out, (cudaStream_t)stream, d_sums, hp, words, vals);
+    }
     launches += pdwt_launch_count() - before;
     if (rc < 0) last_error = rc;
     return rc;
