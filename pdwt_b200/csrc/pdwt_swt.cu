@@ -9,9 +9,11 @@
 // instead of TH + (hlen-1)*f.  Along x the tile is a contiguous run of columns (coalesced global accesses) plus the
 // dilated halo of (hlen-1)*f columns.
 //
-//   forward :  S_in[R][TW + (hlen-1) f]  --row pass-->  S_lo, S_hi [R][TW]  --column pass-->  A, H, V, D
-//   inverse :  {A,H} then {V,D} tiles [R][TW + (hlen-1) f]  --column pass-->  S_t1, S_t2 [TH][TW + (hlen-1) f]
+//   forward :  S_in[R][TW + (hlen-1) f]  --row pass-->  (lo, hi) pairs [R][TW]  --column pass-->  A, H, V, D
+//   inverse :  (A,H) then (V,D) pair tiles [R][TW + (hlen-1) f]  --column pass-->  (t1, t2) pairs [TH][TW + (hlen-1) f]
 //              --row pass-->  image
+// Values that are multiplied by the same tap pair sit next to each other in shared memory, so one 64-bit load
+// delivers the packed operand of an FFMA2 / FMUL2.
 //
 // Arithmetic is the reference's, bit for bit: forward = one fmaf chain from 0 over ascending j
 // (separable.cu:427-445, 470-489); inverse = round(v*k), exact halving, add, the two branch sums added last
@@ -57,6 +59,16 @@ __device__ __forceinline__ u64 sw_fmul2(u64 a, u64 b)
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// a + b on both halves, rounded once, as an FFMA2 whose multiplicand `ones` = (1, 1) arrives as a KERNEL PARAMETER:
+// a * 1 is exact, so this IS add.rn.  ptxas contracts a packed product with the packed add behind it into one FFMA2 --
+// for add.rn.f32x2 and also for an fma with the literal (1, 1), even with --fmad=false (seen in the SASS) -- which
+// would round once where the reference rounds twice; a multiplicand it cannot see through keeps the two roundings.
+__device__ __forceinline__ u64 sw_add2_exact(u64 a, u64 ones, u64 b)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(ones), "l"(b));
+    return d;
+}
 __device__ __forceinline__ u64 sw_fadd2(u64 a, u64 b)
 {
     u64 d;
@@ -71,6 +83,16 @@ __device__ __forceinline__ int wrap1(int i, int N)   // fold_swt as a function o
     return min(max(i, 0), N - 1);   // only indices of masked outputs can still be outside
 }
 
+// Row passes with compile-time dilation F <= 8: a thread produces the 4 outputs x0, x0 + F, x0 + 2F, x0 + 3F of one tile
+// row -- they share all but one of their taps' samples, so hlen + 3 shared-memory loads serve 4 hlen taps.  The lanes of
+// a warp (4-byte samples; half-warp for 8-byte pairs) are spread over NB/4 or F columns x0 = r + 4F g (r < F) of several
+// rows; with a row pitch congruent to F modulo the number of banks NB (32 x 4 bytes, 16 x 8 bytes) every load of the
+// warp touches each bank once.
+__host__ __device__ constexpr int swt_pitch(int width, int f, int nbanks)
+{
+    return (f >= 1 && f <= 8) ? width + (((f - width) % nbanks) + nbanks) % nbanks : width;
+}
+
 // ================================================================================================== forward
 template <int HLEN>
 struct SwtFwdCfg {
@@ -78,7 +100,7 @@ struct SwtFwdCfg {
     static constexpr int C = HLEN / 2 - 1;          // centre_fwd for even hlen (separable.cu:417-421), in units of f
     static constexpr int R = TH + HLEN - 1;         // staged rows (one residue class)
     static constexpr int RPT = 4;                   // output rows per column-pass task
-    static size_t smem(int f) { return sizeof(float) * ((size_t)R * (TW + (HLEN - 1) * f) + 2 * (size_t)R * TW); }
+    static size_t smem(int f) { return sizeof(float) * ((size_t)R * swt_pitch(TW + (HLEN - 1) * f, f, 32) + 1 + 2 * (size_t)R * TW); }
 };
 
 // F = compile-time dilation (tap offsets become immediates), 0 = run-time `f_rt`
@@ -91,10 +113,9 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
     using K = SwtFwdCfg<HLEN>;
     const int f = F ? F : f_rt;
     extern __shared__ __align__(16) float smem[];
-    const int pitch = K::TW + (HLEN - 1) * f;
+    const int width = K::TW + (HLEN - 1) * f, pitch = swt_pitch(width, f, 32);
     float* S_in = smem;
-    float* S_lo = smem + K::R * pitch;
-    float* S_hi = S_lo + K::R * K::TW;
+    u64* S_lh = reinterpret_cast<u64*>(smem + ((K::R * pitch + 1) & ~1));   // [R][TW] (lo, hi) pairs, 8-byte aligned
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ry = blockIdx.y % f, mt = blockIdx.y / f;
     const int gx0 = blockIdx.x * K::TW;
@@ -102,29 +123,66 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
     pdl_wait();
 
     // ---- stage the tile: row t of the tile is image row ry + f*(mt*TH + t - C), column u is gx0 - C*f + u
+    // Tiles whose columns need no fold (all but the first and last of a row of tiles) take the copies with immediate
+    // offsets, one LDGSTS per 32 columns; the others fold every column index (separable.cu:428-433).
+    const int xs = gx0 - K::C * f;
+    const bool interior = F != 0 && xs >= 0 && xs + width <= Nc;
     for (int r = warp; r < K::R; r += kSwtThreads / 32) {
         const int gy = wrap1(ry + f * (mt * K::TH + r - K::C), Nr);
         const float* row = src + (size_t)gy * Nc;
-        for (int u = lane; u < pitch; u += 32) cp_async4(S_in + r * pitch + u, row + wrap1(gx0 - K::C * f + u, Nc));
+        if (interior) {
+            constexpr int WC = K::TW + (HLEN - 1) * F;   // = width
+            const float* g = row + xs + lane;
+            float* d = S_in + r * pitch + lane;
+#pragma unroll
+            for (int k = 0; k < (WC + 31) / 32; k++)
+                if (32 * k + 31 < WC || 32 * k + lane < WC) cp_async4(d + 32 * k, g + 32 * k);
+        } else {
+            for (int u = lane; u < width; u += 32) cp_async4(S_in + r * pitch + u, row + wrap1(xs + u, Nc));
+        }
     }
     cp_async_wait_all0();
     __syncthreads();
 
     // ---- row pass, w_kern_forward_swt_pass1 (separable.cu:409-448): lo/hi[x] = sum_j in[x + (j - C) f] * L/H[hlen-1-j]
-    for (int r = warp; r < K::R; r += kSwtThreads / 32) {
+    if (F >= 1 && F <= 8) {
+        // 4 outputs F apart per thread (see swt_pitch): a warp takes 4 rows x 32 columns
+        constexpr int FF = F ? F : 1;
+        const int l8 = lane & 7, mrow = lane >> 3;
+        const int xl = (l8 % FF) + 4 * FF * (l8 / FF);
+        constexpr int NCH = K::TW / 32;
+        for (int item = warp; item < ((K::R + 3) / 4) * NCH; item += kSwtThreads / 32) {
+            const int r = (item / NCH) * 4 + mrow, x0 = (item % NCH) * 32 + xl;
+            if (r < K::R) {
+                const float* p = S_in + r * pitch + x0;
+                u64 lh[4] = {0ull, 0ull, 0ull, 0ull};   // (lo, hi) += v * (L, H)[hlen-1-j], j ascending for every output
 #pragma unroll
-        for (int xx = lane; xx < K::TW; xx += 32) {
-            const float* p = S_in + r * pitch + xx;
-            u64 lh = 0ull;   // (lo, hi) += v * (L, H)[hlen-1-j]
+                for (int i = 0; i < HLEN + 3; i++) {
+                    const float v = p[i * FF];
+                    const u64 vv = sw_pack2(v, v);
 #pragma unroll
-            for (int j = 0; j < HLEN; j++) {
-                const float v = p[j * f];
-                lh = sw_ffma2(sw_pack2(v, v), sw_pack2(t.L[HLEN - 1 - j], t.H[HLEN - 1 - j]), lh);
+                    for (int o = 0; o < 4; o++) {
+                        const int j = i - o;
+                        if (j >= 0 && j < HLEN) lh[o] = sw_ffma2(vv, sw_pack2(t.L[HLEN - 1 - j], t.H[HLEN - 1 - j]), lh[o]);
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < 4; o++) S_lh[r * K::TW + x0 + o * FF] = lh[o];
             }
-            float lo, hi;
-            sw_unpack2(lh, lo, hi);
-            S_lo[r * K::TW + xx] = lo;
-            S_hi[r * K::TW + xx] = hi;
+        }
+    } else {
+        for (int r = warp; r < K::R; r += kSwtThreads / 32) {
+#pragma unroll
+            for (int xx = lane; xx < K::TW; xx += 32) {
+                const float* p = S_in + r * pitch + xx;
+                u64 lh = 0ull;   // (lo, hi) += v * (L, H)[hlen-1-j]
+#pragma unroll
+                for (int j = 0; j < HLEN; j++) {
+                    const float v = p[j * f];
+                    lh = sw_ffma2(sw_pack2(v, v), sw_pack2(t.L[HLEN - 1 - j], t.H[HLEN - 1 - j]), lh);
+                }
+                S_lh[r * K::TW + xx] = lh;
+            }
         }
     }
     __syncthreads();
@@ -140,7 +198,8 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
         for (int o = 0; o < K::RPT; o++) ah[o] = vd[o] = 0ull;
 #pragma unroll
         for (int i = 0; i < K::RPT + HLEN - 1; i++) {
-            const float v1 = S_lo[(m0 + i) * K::TW + xx], v2 = S_hi[(m0 + i) * K::TW + xx];
+            float v1, v2;
+            sw_unpack2(S_lh[(m0 + i) * K::TW + xx], v1, v2);
             const u64 p1 = sw_pack2(v1, v1), p2 = sw_pack2(v2, v2);
 #pragma unroll
             for (int o = 0; o < K::RPT; o++) {
@@ -177,7 +236,7 @@ struct SwtInvCfg {
     static constexpr int R = TH + HLEN - 1;
     static constexpr int RPT = 4;
     // two coefficient tiles + t1 + t2, all CI = TW + (hlen-1) f columns wide
-    static size_t smem(int f) { return sizeof(float) * (2 * (size_t)R + 2 * (size_t)TH) * (TW + (HLEN - 1) * f); }
+    static size_t smem(int f) { return sizeof(float) * (2 * (size_t)R + 2 * (size_t)TH) * swt_pitch(TW + (HLEN - 1) * f, f, 16); }
 };
 
 // One synthesis tap of the reference: res += v * k / 2 = round(v*k), exact halving, add (separable.cu:581-584).  Halving
@@ -189,6 +248,7 @@ struct SwtInvCfg {
 template <int HLEN>
 struct SwtHalfTaps {
     float2 k[HLEN];   // (IL, IH)[hlen-1-j] / 2, exact
+    float2 one;       // (1, 1), opaque to the compiler (see sw_add2_exact)
 };
 template <int HLEN, int F>
 __global__ void __launch_bounds__(kSwtThreads, 2)
@@ -199,11 +259,12 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
     using K = SwtInvCfg<HLEN>;
     const int f = F ? F : f_rt;
     auto khalf = [&](const int j) { return sw_pack2(t.k[j].x, t.k[j].y); };
+    const u64 ones = sw_pack2(t.one.x, t.one.y);
     extern __shared__ __align__(16) float smem[];
     const int ci = K::TW + (HLEN - 1) * f;           // columns of t1/t2 the row pass of this tile reads
-    float* S_c0 = smem;                              // A, then V
-    float* S_c1 = S_c0 + K::R * ci;                  // H, then D
-    float* S_t = S_c1 + K::R * ci;                   // [2][TH][ci]: t1, t2
+    const int cip = swt_pitch(ci, f, 16);            // row pitch of the pair tiles (elements of 8 bytes)
+    float* S_c = smem;                               // [R][cip] pairs (A, H), then (V, D)
+    float* S_t = S_c + 2 * K::R * cip;               // [TH][cip] pairs (t1, t2)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ry = blockIdx.y % f, mt = blockIdx.y / f;
     const int gx0 = blockIdx.x * K::TW;
@@ -213,42 +274,57 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
     for (int pair = 0; pair < 2; pair++) {
         const float* c0 = (pair ? V + (size_t)blockIdx.z * s_d : A + (size_t)blockIdx.z * s_a);
         const float* c1 = (pair ? D : H) + (size_t)blockIdx.z * s_d;
-        if (pair) __syncthreads();   // the column pass of the first pair has finished reading S_c0 / S_c1
+        if (pair) __syncthreads();   // the column pass of the first pair has finished reading S_c
+        const int xs = gx0 - K::C * f;
+        const bool interior = F != 0 && xs >= 0 && xs + ci <= Nc;   // no column fold: copies with immediate offsets
         for (int r = warp; r < K::R; r += kSwtThreads / 32) {
             const size_t rowo = (size_t)wrap1(ry + f * (mt * K::TH + r - K::C), Nr) * Nc;
-            for (int u = lane; u < ci; u += 32) {
-                const size_t o = rowo + wrap1(gx0 - K::C * f + u, Nc);
-                cp_async4(S_c0 + r * ci + u, c0 + o);
-                cp_async4(S_c1 + r * ci + u, c1 + o);
+            if (interior) {
+                constexpr int WC = K::TW + (HLEN - 1) * F;   // = ci
+                const float* g0 = c0 + rowo + xs + lane;
+                const float* g1 = c1 + rowo + xs + lane;
+                float* d = S_c + 2 * (r * cip + lane);
+#pragma unroll
+                for (int k = 0; k < (WC + 31) / 32; k++)
+                    if (32 * k + 31 < WC || 32 * k + lane < WC) {
+                        cp_async4(d + 64 * k, g0 + 32 * k);
+                        cp_async4(d + 64 * k + 1, g1 + 32 * k);
+                    }
+            } else {
+                for (int u = lane; u < ci; u += 32) {
+                    const size_t o = rowo + wrap1(xs + u, Nc);
+                    cp_async4(S_c + 2 * (r * cip + u), c0 + o);
+                    cp_async4(S_c + 2 * (r * cip + u) + 1, c1 + o);
+                }
             }
         }
         cp_async_wait_all0();
         __syncthreads();
         // column pass, w_kern_inverse_swt_pass1 (separable.cu:553-589): t = IL_y(c0) + IH_y(c1), RPT rows per task
-        float* S_out = S_t + pair * K::TH * ci;
+        float* S_out = S_t + pair;   // t1 in the even words, t2 in the odd ones
         const int ncb = (ci + 31) / 32;
         for (int task = warp; task < ncb * (K::TH / K::RPT); task += kSwtThreads / 32) {
             const int u = (task % ncb) * 32 + lane, m0 = (task / ncb) * K::RPT;
             if (u < ci) {
-                float rl[K::RPT], rh[K::RPT];
+                u64 rlh[K::RPT];   // (rl, rh)
 #pragma unroll
-                for (int o = 0; o < K::RPT; o++) rl[o] = rh[o] = 0.f;
+                for (int o = 0; o < K::RPT; o++) rlh[o] = 0ull;
 #pragma unroll
                 for (int i = 0; i < K::RPT + HLEN - 1; i++) {
-                    const u64 v01 = sw_pack2(S_c0[(m0 + i) * ci + u], S_c1[(m0 + i) * ci + u]);
+                    const u64 v01 = reinterpret_cast<const u64*>(S_c)[(m0 + i) * cip + u];
 #pragma unroll
                     for (int o = 0; o < K::RPT; o++) {
                         const int j = i - o;
-                        if (j >= 0 && j < HLEN) {
-                            float pl, ph;   // the two products rounded on their own (one FMUL2), then two plain adds
-                            sw_unpack2(sw_fmul2(v01, khalf(j)), pl, ph);
-                            rl[o] = __fadd_rn(rl[o], pl);
-                            rh[o] = __fadd_rn(rh[o], ph);
-                        }
+                        // the two products rounded on their own (one FMUL2), then added (see sw_add2_exact)
+                        if (j >= 0 && j < HLEN) rlh[o] = sw_add2_exact(sw_fmul2(v01, khalf(j)), ones, rlh[o]);
                     }
                 }
 #pragma unroll
-                for (int o = 0; o < K::RPT; o++) S_out[(m0 + o) * ci + u] = __fadd_rn(rl[o], rh[o]);
+                for (int o = 0; o < K::RPT; o++) {
+                    float rl, rh;
+                    sw_unpack2(rlh[o], rl, rh);
+                    S_out[2 * ((m0 + o) * cip + u)] = __fadd_rn(rl, rh);
+                }
             }
         }
     }
@@ -257,23 +333,59 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
 
     // ---- row pass, w_kern_inverse_swt_pass2 (separable.cu:593-626): img[x] = IL_x(t1) + IH_x(t2), taps f apart
     dst += (size_t)blockIdx.z * s_dst;
-    const float* S_t1 = S_t;
-    const float* S_t2 = S_t + K::TH * ci;
-    const int xx = tid % K::TW;
-    const int gx = gx0 + xx;
-    for (int m = tid / K::TW; m < K::TH; m += kSwtThreads / K::TW) {
-        const float* p1 = S_t1 + m * ci + xx;
-        const float* p2 = S_t2 + m * ci + xx;
-        float a1 = 0.f, a2 = 0.f;
+    const u64* S_t12 = reinterpret_cast<const u64*>(S_t);
+    if (F >= 1 && F <= 8) {
+        // 4 outputs F apart per thread (see swt_pitch): a warp takes 8 rows x 16 columns (F <= 4) or 4 rows x 32 columns
+        constexpr int FF = F ? F : 1;
+        constexpr int LPR = FF < 4 ? 4 : FF, RPW = 32 / LPR, CW = 4 * LPR, NCH = K::TW / CW;
+        const int ll = lane % LPR, mrow = lane / LPR;
+        const int xl = (ll % FF) + 4 * FF * (ll / FF);
+        const bool vec_ok = FF == 1 && (Nc & 3) == 0 && (s_dst & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+        for (int item = warp; item < (K::TH / RPW) * NCH; item += kSwtThreads / 32) {
+            const int m = (item / NCH) * RPW + mrow, x0 = (item % NCH) * CW + xl;
+            const u64* p12 = S_t12 + m * cip + x0;
+            u64 acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-        for (int j = 0; j < HLEN; j++) {
-            float q1, q2;
-            sw_unpack2(sw_fmul2(sw_pack2(p1[j * f], p2[j * f]), khalf(j)), q1, q2);
-            a1 = __fadd_rn(a1, q1);
-            a2 = __fadd_rn(a2, q2);
+            for (int i = 0; i < HLEN + 3; i++) {
+                const u64 v12 = p12[i * FF];
+#pragma unroll
+                for (int o = 0; o < 4; o++) {
+                    const int j = i - o;
+                    if (j >= 0 && j < HLEN) acc[o] = sw_add2_exact(sw_fmul2(v12, khalf(j)), ones, acc[o]);
+                }
+            }
+            float res[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                float a1, a2;
+                sw_unpack2(acc[o], a1, a2);
+                res[o] = __fadd_rn(a1, a2);
+            }
+            const int gy = ry + f * (mt * K::TH + m), gx = gx0 + x0;
+            if (gy < Nr) {
+                float* q = dst + (size_t)gy * Nc + gx;
+                if (vec_ok && gx + 3 < Nc) {
+                    *reinterpret_cast<float4*>(q) = make_float4(res[0], res[1], res[2], res[3]);
+                } else {
+#pragma unroll
+                    for (int o = 0; o < 4; o++)
+                        if (gx + o * FF < Nc) q[o * FF] = res[o];
+                }
+            }
         }
-        const int gy = ry + f * (mt * K::TH + m);
-        if (gy < Nr && gx < Nc) dst[(size_t)gy * Nc + gx] = __fadd_rn(a1, a2);
+    } else {
+        const int xx = tid % K::TW;
+        const int gx = gx0 + xx;
+        for (int m = tid / K::TW; m < K::TH; m += kSwtThreads / K::TW) {
+            const u64* p12 = S_t12 + m * cip + xx;
+            u64 a12 = 0ull;
+#pragma unroll
+            for (int j = 0; j < HLEN; j++) a12 = sw_add2_exact(sw_fmul2(p12[j * f], khalf(j)), ones, a12);
+            float a1, a2;
+            sw_unpack2(a12, a1, a2);
+            const int gy = ry + f * (mt * K::TH + m);
+            if (gy < Nr && gx < Nc) dst[(size_t)gy * Nc + gx] = __fadd_rn(a1, a2);
+        }
     }
 }
 
@@ -327,6 +439,7 @@ static int launch_swt_inv(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D,
     PDWT_PROF(prof_tag("k_swt_inv_fused", Nr, f), s);
     SwtHalfTaps<HLEN> ht;
     for (int j = 0; j < HLEN; j++) ht.k[j] = make_float2(t.IL[HLEN - 1 - j] * 0.5f, t.IH[HLEN - 1 - j] * 0.5f);
+    ht.one = make_float2(1.0f, 1.0f);
 #define PDWT_SWT_INV(FF)                                                                                                 \
     do {                                                                                                                 \
         static PerDeviceOnce once;                                                                                       \
