@@ -155,7 +155,9 @@ struct NsInvCfg {
     static constexpr int TWC = 64, THC = 8;           // coefficient tile: 32 thread columns x 8 rows
     static constexpr int INR = THC + WIN - 1;
     static constexpr int INW = TWC + WIN - 1;
-    static constexpr int PITCH = INW + 1;             // in float2 pairs
+    static constexpr int PITCH = INW;                 // in float2 pairs; even (WIN is odd), so a thread's window is 16-byte aligned
+    static constexpr int NW = WIN + P - 1;            // window columns of a thread (both positions); even
+    static_assert(P == 2 && (PITCH % 2) == 0 && (NW % 2) == 0 && ((INR * PITCH) % 2) == 0, "128-bit window loads");
     // (A,H) tile + (V,D) tile as float2, then K'[ey][ex][jy][jx] as float4
     static constexpr size_t SMEM = sizeof(float2) * 2 * (size_t)INR * PITCH + sizeof(float4) * 4 * H2 * H2;
 };
@@ -212,27 +214,38 @@ __global__ void __launch_bounds__(kNsThreads, 2)
         for (int e = 0; e < 4; e++) rah[p][e >> 1][e & 1] = rvd[p][e >> 1][e & 1] = 0ull;
     const float2* wah = S_ah + ty * K::PITCH + K::P * tx;
     const float2* wvd = S_vd + ty * K::PITCH + K::P * tx;
+    // Shared-memory traffic is what bounds this kernel (ncu: mio_throttle, 1 wavefront per clock and SM), so a window
+    // row is fetched with 128-bit loads (two (A,H) or (V,D) pairs each: dense 512 bytes per warp) and every filter
+    // quadruple K' is fetched ONCE and applied to both positions of the thread.
 #pragma unroll 1
     for (int dy = 0; dy < WIN; dy++) {
+        u64 dah[K::NW], dvd[K::NW];   // window column dx of position 0 = column dx-1 of position 1
 #pragma unroll
-        for (int dx = 0; dx < WIN + K::P - 1; dx++) {   // window column dx of position 0 = column dx-1 of position 1
-            const float2 ah = wah[dy * K::PITCH + dx], vd = wvd[dy * K::PITCH + dx];
-            const u64 dah = ns_pack2(ah.x, ah.y), dvd = ns_pack2(vd.x, vd.y);
+        for (int q = 0; q < K::NW / 2; q++) {
+            const float4 f = *reinterpret_cast<const float4*>(wah + dy * K::PITCH + 2 * q);
+            const float4 g = *reinterpret_cast<const float4*>(wvd + dy * K::PITCH + 2 * q);
+            dah[2 * q] = ns_pack2(f.x, f.y);
+            dah[2 * q + 1] = ns_pack2(f.z, f.w);
+            dvd[2 * q] = ns_pack2(g.x, g.y);
+            dvd[2 * q + 1] = ns_pack2(g.z, g.w);
+        }
 #pragma unroll
-            for (int ey = 0; ey < 2; ey++) {
-                const int jy = dy - (ey ? SHIFT : 0);   // run-time (dy is), uniform
-                if (jy < 0 || jy >= H2) continue;
+        for (int ey = 0; ey < 2; ey++) {
+            const int jy = dy - (ey ? SHIFT : 0);   // run-time (dy is), uniform
+            if (jy < 0 || jy >= H2) continue;
 #pragma unroll
-                for (int p = 0; p < K::P; p++)
+            for (int ex = 0; ex < 2; ex++)
 #pragma unroll
-                    for (int ex = 0; ex < 2; ex++) {
-                        const int jx = dx - p - (ex ? SHIFT : 0);
-                        if (jx < 0 || jx >= H2) continue;   // compile-time
-                        const float4 k = S_k[((ey * 2 + ex) * H2 + jy) * H2 + jx];
-                        rah[p][ey][ex] = ns_ffma2(dah, ns_pack2(k.x, k.y), rah[p][ey][ex]);
-                        rvd[p][ey][ex] = ns_ffma2(dvd, ns_pack2(k.z, k.w), rvd[p][ey][ex]);
+                for (int jx = 0; jx < H2; jx++) {   // ascending (jy, jx) for every output: the reference's order
+                    const float4 k = S_k[((ey * 2 + ex) * H2 + jy) * H2 + jx];
+                    const u64 k01 = ns_pack2(k.x, k.y), k23 = ns_pack2(k.z, k.w);
+#pragma unroll
+                    for (int p = 0; p < K::P; p++) {
+                        const int dx = jx + p + (ex ? SHIFT : 0);
+                        rah[p][ey][ex] = ns_ffma2(dah[dx], k01, rah[p][ey][ex]);
+                        rvd[p][ey][ex] = ns_ffma2(dvd[dx], k23, rvd[p][ey][ex]);
                     }
-            }
+                }
         }
     }
     img += (size_t)blockIdx.z * s_img;
