@@ -153,29 +153,38 @@ struct NsInvCfg {
     static constexpr int WIN = H2 + SHIFT;            // coefficient window behind one 2x2 output block, per axis
     static constexpr int P = 2;                       // coefficient positions (along x) per thread
     static constexpr int TWC = 64, THC = 8;           // coefficient tile: 32 thread columns x 8 rows
-    static constexpr int INR = THC + WIN - 1;
     static constexpr int INW = TWC + WIN - 1;
     static constexpr int PITCH = INW;                 // in float2 pairs; even (WIN is odd), so a thread's window is 16-byte aligned
     static constexpr int NW = WIN + P - 1;            // window columns of a thread (both positions); even
-    static_assert(P == 2 && (PITCH % 2) == 0 && (NW % 2) == 0 && ((INR * PITCH) % 2) == 0, "128-bit window loads");
+    static_assert(P == 2 && (PITCH % 2) == 0 && (NW % 2) == 0, "128-bit window loads");
+    static constexpr int MAXRG = 4;                   // a CTA stages once for up to MAXRG groups of THC coefficient rows
     // (A,H) tile + (V,D) tile as float2, then K'[ey][ex][jy][jx] as float4
-    static constexpr size_t SMEM = sizeof(float2) * 2 * (size_t)INR * PITCH + sizeof(float4) * 4 * H2 * H2;
+    static constexpr size_t smem(int rg) { return sizeof(float2) * 2 * (size_t)(rg * THC + WIN - 1) * PITCH + sizeof(float4) * 4 * H2 * H2; }
 };
+
+// 4-byte asynchronous copy global -> shared: no register staging, the whole tile in flight at once
+__device__ __forceinline__ void ns_cp4(float* smem_dst, const float* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(src)
+                 : "memory");
+}
 
 template <int HLEN>
 __global__ void __launch_bounds__(kNsThreads, 2)
     k_nonsep_inv_tiled(const __grid_constant__ Taps t, float* __restrict__ img, size_t s_img, const float* __restrict__ A,
                        size_t s_a, const float* __restrict__ H, const float* __restrict__ V, const float* __restrict__ D,
-                       size_t s_d, int Nr, int Nc, int Nr2, int Nc2)   // Nr x Nc coefficients -> Nr2 x Nc2 pixels
+                       size_t s_d, int Nr, int Nc, int Nr2, int Nc2,   // Nr x Nc coefficients -> Nr2 x Nc2 pixels
+                       int rg)                                          // groups of THC coefficient rows per CTA
 {
     using K = NsInvCfg<HLEN>;
     constexpr int H2 = K::H2, SHIFT = K::SHIFT, WIN = K::WIN;
     extern __shared__ __align__(16) float smem[];
+    const int inr = rg * K::THC + WIN - 1;          // staged rows: the halo is paid once for rg row groups
     float2* S_ah = reinterpret_cast<float2*>(smem);
-    float2* S_vd = S_ah + K::INR * K::PITCH;
-    float4* S_k = reinterpret_cast<float4*>(S_vd + K::INR * K::PITCH);   // [ey][ex][jy][jx] -> (LL', LH', HL', HH')
+    float2* S_vd = S_ah + inr * K::PITCH;
+    float4* S_k = reinterpret_cast<float4*>(S_vd + inr * K::PITCH);   // [ey][ex][jy][jx] -> (LL', LH', HL', HH')
     const int tid = threadIdx.x;
-    const int cx0 = blockIdx.x * K::TWC, cy0 = blockIdx.y * K::THC;
+    const int cx0 = blockIdx.x * K::TWC, cy0 = blockIdx.y * (K::THC * rg);
 
     // synthesis products per output parity e (0 = even output index): tap j multiplies I?[hlen-1-(2j+off_e)] with
     // off_e = e ? SHIFT : 1-SHIFT (nonseparable.cu:186-204)
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(kNsThreads, 2)
     const float* pv = V + (size_t)blockIdx.z * s_d;
     const float* pd = D + (size_t)blockIdx.z * s_d;
     // coefficient tiles with the reference's single periodic wrap (nonseparable.cu:205-214), interleaved in pairs
-    for (int i = tid; i < K::INR * K::INW; i += kNsThreads) {
+    for (int i = tid; i < inr * K::INW; i += kNsThreads) {
         const int r = i / K::INW, u = i - r * K::INW;
         int y = cy0 - K::CC + r, x = cx0 - K::CC + u;
         y += (y < 0) ? Nr : 0;
@@ -200,13 +209,23 @@ __global__ void __launch_bounds__(kNsThreads, 2)
         x += (x < 0) ? Nc : 0;
         x -= (x >= Nc) ? Nc : 0;
         const size_t o = (size_t)ns_clamp(y, Nr - 1) * Nc + ns_clamp(x, Nc - 1);
-        S_ah[r * K::PITCH + u] = make_float2(__ldg(pa + o), __ldg(ph + o));
-        S_vd[r * K::PITCH + u] = make_float2(__ldg(pv + o), __ldg(pd + o));
+        float* dah = reinterpret_cast<float*>(S_ah + r * K::PITCH + u);
+        float* dvd = reinterpret_cast<float*>(S_vd + r * K::PITCH + u);
+        ns_cp4(dah, pa + o);
+        ns_cp4(dah + 1, ph + o);
+        ns_cp4(dvd, pv + o);
+        ns_cp4(dvd + 1, pd + o);
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     pdl_launch_dependents();
 
-    const int tx = tid % (K::TWC / K::P), ty = tid / (K::TWC / K::P);
+    const int tx = tid % (K::TWC / K::P), ty0 = tid / (K::TWC / K::P);
+    img += (size_t)blockIdx.z * s_img;
+#pragma unroll 1
+    for (int g = 0; g < rg; g++) {
+    const int ty = ty0 + g * K::THC;
+    if (cy0 + ty >= Nr) break;               // warp-uniform: a warp is one tile row
     u64 rah[K::P][2][2], rvd[K::P][2][2];   // [position][ey][ex] -> (ra, rh), (rv, rd)
 #pragma unroll
     for (int p = 0; p < K::P; p++)
@@ -248,7 +267,6 @@ __global__ void __launch_bounds__(kNsThreads, 2)
                 }
         }
     }
-    img += (size_t)blockIdx.z * s_img;
 #pragma unroll
     for (int ey = 0; ey < 2; ey++) {
         const int gy = 2 * (cy0 + ty) + ey;
@@ -265,6 +283,7 @@ __global__ void __launch_bounds__(kNsThreads, 2)
                 img[(size_t)gy * Nc2 + gx] = __fadd_rn(__fadd_rn(__fadd_rn(ra, rh), rv), rd);
             }
     }
+    }   // row groups
 }
 
 // ================================================================================================ launchers
@@ -294,13 +313,22 @@ static int launch_ns_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
     if (Nr < K::WIN || Nc < K::WIN) return 0;   // the single wrap must suffice
     static PerDeviceOnce once;
     if (once.first()) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_inv_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_inv_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)K::smem(K::MAXRG)));
     }
-    dim3 grid(idiv_up(Nc, K::TWC), idiv_up(Nr, K::THC), batch);
+    // Row groups per CTA: more groups amortise the staged halo (WIN - 1 rows) and the staging latency over more
+    // arithmetic, as long as the grid still fills the GPU several times over (2 CTAs per SM are resident).
+    int rg = K::MAXRG;
+    if (const char* e = getenv("PDWT_NS_RG")) rg = atoi(e);
+    else
+        while (rg > 1 && (long long)idiv_up(Nc, K::TWC) * idiv_up(Nr, K::THC * rg) * batch < 3LL * 2 * 148) rg >>= 1;
+    if (rg < 1) rg = 1;
+    if (rg > K::MAXRG) rg = K::MAXRG;
+    dim3 grid(idiv_up(Nc, K::TWC), idiv_up(Nr, K::THC * rg), batch);
     if (grid.y > 65535u) return 0;
     PDWT_PROF(prof_tag("k_nonsep_inv_tiled", Nr2, Nc2), s);
-    PDWT_CUDA(launch_pdl(k_nonsep_inv_tiled<HLEN>, grid, kNsThreads, K::SMEM, s, t, img.p, img.stride, (const float*)A.p,
-                         A.stride, (const float*)H.p, (const float*)V.p, (const float*)D.p, H.stride, Nr, Nc, Nr2, Nc2));
+    PDWT_CUDA(launch_pdl(k_nonsep_inv_tiled<HLEN>, grid, kNsThreads, K::smem(rg), s, t, img.p, img.stride, (const float*)A.p,
+                         A.stride, (const float*)H.p, (const float*)V.p, (const float*)D.p, H.stride, Nr, Nc, Nr2, Nc2, rg));
     PDWT_LAUNCH_CHECK();
     return 1;
 }
