@@ -42,6 +42,13 @@ __device__ __forceinline__ int ns_clamp(int v, int hi) { return v < 0 ? 0 : (v >
 
 constexpr int kNsThreads = 256;
 
+// 4-byte asynchronous copy global -> shared: no register staging, the whole tile in flight at once
+__device__ __forceinline__ void ns_cp4(float* smem_dst, const float* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(src)
+                 : "memory");
+}
+
 // ================================================================================================== forward
 template <int HLEN>
 struct NsFwdCfg {
@@ -51,9 +58,15 @@ struct NsFwdCfg {
     static constexpr int INR = 2 * TH + HLEN - 2;
     static constexpr int INW = 2 * TW + HLEN - 2;
     static constexpr int NV = (2 * (U - 1) + HLEN + 3) / 4;   // 16-byte vectors a thread reads per tap row
-    static constexpr int PITCH = ((2 * (TW - U) + 4 * NV + 3) / 4) * 4 + 4;   // floats; >= INW, multiple of 4
+    static constexpr int PITCH = ((2 * (TW - U) + 4 * NV + 7) / 8) * 8 + 8;   // floats; >= INW, multiple of 8
+    // A thread's window starts at 16-byte vector 2 tx of its row: read in place, the lanes of a warp would be 32 bytes
+    // apart (half the shared-memory bandwidth).  So a row is stored with its EVEN vectors first and its odd vectors
+    // behind them (HALF vectors each): window vector i of lane tx is vector (i & 1) * HALF + tx + (i >> 1), consecutive
+    // lanes read consecutive 16 bytes.
+    static constexpr int HALF = PITCH / 8;
     static constexpr size_t SMEM = sizeof(float) * ((size_t)INR * PITCH + 4 * HLEN * HLEN);
-    static_assert(PITCH >= INW, "tile pitch");
+    static_assert(PITCH >= INW && 2 * (TW / U - 1) + NV <= PITCH / 4, "tile pitch");
+    __host__ __device__ static constexpr int slot(int u) { return ((((u >> 2) & 1) * HALF + (u >> 3)) << 2) + (u & 3); }
 };
 
 template <int HLEN>
@@ -79,11 +92,26 @@ __global__ void __launch_bounds__(kNsThreads, 2)
     }
     pdl_wait();
     // input tile with the reference's fold (periodic; odd sizes repeat the last sample), nonseparable.cu:139-152
-    for (int i = tid; i < K::INR * K::PITCH; i += kNsThreads) {
-        const int r = i / K::PITCH, u = i - r * K::PITCH;
-        const int y = ns_clamp(fold_dec(2 * gy0 - K::C + r, Nr), Nr - 1);
-        const int x = ns_clamp(fold_dec(2 * gx0 - K::C + u, Nc), Nc - 1);
-        S_in[i] = __ldg(img + (size_t)y * Nc + x);
+    // (asynchronous 4-byte copies: the whole tile is in flight at once; a warp takes a row, the row fold is applied once
+    // per row and the column fold only by the tiles at the left and right edge)
+    {
+        const int xs = 2 * gx0 - K::C;
+        const bool interior = xs >= 0 && xs + K::INW <= Nc;
+        const int lane = tid & 31;
+        for (int r = tid >> 5; r < K::INR; r += kNsThreads / 32) {
+            const float* row = img + (size_t)ns_clamp(fold_dec(2 * gy0 - K::C + r, Nr), Nr - 1) * Nc;
+            float* d = S_in + r * K::PITCH;
+            if (interior) {
+#pragma unroll
+                for (int k = 0; k < (K::INW + 31) / 32; k++) {
+                    const int u = 32 * k + lane;
+                    if (32 * k + 31 < K::INW || u < K::INW) ns_cp4(d + K::slot(u), row + xs + u);
+                }
+            } else {
+                for (int u = lane; u < K::INW; u += 32) ns_cp4(d + K::slot(u), row + ns_clamp(fold_dec(xs + u, Nc), Nc - 1));
+            }
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     pdl_launch_dependents();
@@ -92,14 +120,15 @@ __global__ void __launch_bounds__(kNsThreads, 2)
     u64 aAH[K::U], aVD[K::U];
 #pragma unroll
     for (int u = 0; u < K::U; u++) aAH[u] = aVD[u] = 0ull;
-    const float* win = S_in + (2 * ty) * K::PITCH + 2 * K::U * tx;
+    static_assert(K::U == 4, "a thread's window starts at vector 2 tx");
+    const float* win = S_in + (2 * ty) * K::PITCH + 4 * tx;
 #pragma unroll 1
     for (int jy = 0; jy < HLEN; jy++) {
         float x[K::NV * 4];
         const float4* rp = reinterpret_cast<const float4*>(win + jy * K::PITCH);
 #pragma unroll
         for (int i = 0; i < K::NV; i++) {
-            const float4 f = rp[i];
+            const float4 f = rp[(i & 1) * K::HALF + (i >> 1)];
             x[4 * i] = f.x; x[4 * i + 1] = f.y; x[4 * i + 2] = f.z; x[4 * i + 3] = f.w;
         }
         const float4* kp = S_k + jy * HLEN;
@@ -161,13 +190,6 @@ struct NsInvCfg {
     // (A,H) tile + (V,D) tile as float2, then K'[ey][ex][jy][jx] as float4
     static constexpr size_t smem(int rg) { return sizeof(float2) * 2 * (size_t)(rg * THC + WIN - 1) * PITCH + sizeof(float4) * 4 * H2 * H2; }
 };
-
-// 4-byte asynchronous copy global -> shared: no register staging, the whole tile in flight at once
-__device__ __forceinline__ void ns_cp4(float* smem_dst, const float* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(src)
-                 : "memory");
-}
 
 template <int HLEN>
 __global__ void __launch_bounds__(kNsThreads, 2)
