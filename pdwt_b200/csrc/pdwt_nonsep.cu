@@ -64,7 +64,8 @@ struct NsFwdCfg {
     // behind them (HALF vectors each): window vector i of lane tx is vector (i & 1) * HALF + tx + (i >> 1), consecutive
     // lanes read consecutive 16 bytes.
     static constexpr int HALF = PITCH / 8;
-    static constexpr size_t SMEM = sizeof(float) * ((size_t)INR * PITCH + 4 * HLEN * HLEN);
+    static constexpr int MAXRG = 2;                  // a CTA stages once for up to MAXRG groups of TH output rows
+    static constexpr size_t smem(int rg) { return sizeof(float) * ((size_t)(2 * TH * rg + HLEN - 2) * PITCH + 4 * HLEN * HLEN); }
     static_assert(PITCH >= INW && 2 * (TW / U - 1) + NV <= PITCH / 4, "tile pitch");
     __host__ __device__ static constexpr int slot(int u) { return ((((u >> 2) & 1) * HALF + (u >> 3)) << 2) + (u & 3); }
 };
@@ -73,15 +74,16 @@ template <int HLEN>
 __global__ void __launch_bounds__(kNsThreads, 2)
     k_nonsep_fwd_tiled(const __grid_constant__ Taps t, const float* __restrict__ img, size_t s_img, float* __restrict__ A,
                        size_t s_a, float* __restrict__ H, float* __restrict__ V, float* __restrict__ D, size_t s_d, int Nr,
-                       int Nc)
+                       int Nc, int rg)   // rg: groups of TH output rows per CTA
 {
     using K = NsFwdCfg<HLEN>;
     extern __shared__ __align__(16) float smem[];
+    const int inr = 2 * K::TH * rg + HLEN - 2;   // staged rows: the halo is paid once for rg row groups
     float* S_in = smem;
-    float4* S_k = reinterpret_cast<float4*>(smem + K::INR * K::PITCH);   // [jy][jx] -> (LL, LH, HL, HH)
+    float4* S_k = reinterpret_cast<float4*>(smem + inr * K::PITCH);   // [jy][jx] -> (LL, LH, HL, HH)
     const int tid = threadIdx.x;
     const int nr = half_up(Nr), nc = half_up(Nc);
-    const int gx0 = blockIdx.x * K::TW, gy0 = blockIdx.y * K::TH;
+    const int gx0 = blockIdx.x * K::TW, gy0 = blockIdx.y * (K::TH * rg);
     img += (size_t)blockIdx.z * s_img;
 
     // the four 2-D filters in accumulation order: tap (jy, jx) multiplies K[hlen-1-jy][hlen-1-jx] (nonseparable.cu:155-160)
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kNsThreads, 2)
         const int xs = 2 * gx0 - K::C;
         const bool interior = xs >= 0 && xs + K::INW <= Nc;
         const int lane = tid & 31;
-        for (int r = tid >> 5; r < K::INR; r += kNsThreads / 32) {
+        for (int r = tid >> 5; r < inr; r += kNsThreads / 32) {
             const float* row = img + (size_t)ns_clamp(fold_dec(2 * gy0 - K::C + r, Nr), Nr - 1) * Nc;
             float* d = S_in + r * K::PITCH;
             if (interior) {
@@ -116,7 +118,12 @@ __global__ void __launch_bounds__(kNsThreads, 2)
     __syncthreads();
     pdl_launch_dependents();
 
-    const int tx = tid % (K::TW / K::U), ty = tid / (K::TW / K::U);
+    const int tx = tid % (K::TW / K::U), ty0 = tid / (K::TW / K::U);
+#pragma unroll 1
+    for (int g = 0; g < rg; g++) {
+    const int ty = ty0 + g * K::TH;
+    const int gy = gy0 + ty, gx = gx0 + K::U * tx;
+    if (gy >= nr || gx >= nc) continue;   // no barrier below
     u64 aAH[K::U], aVD[K::U];
 #pragma unroll
     for (int u = 0; u < K::U; u++) aAH[u] = aVD[u] = 0ull;
@@ -144,8 +151,6 @@ __global__ void __launch_bounds__(kNsThreads, 2)
             }
         }
     }
-    const int gy = gy0 + ty, gx = gx0 + K::U * tx;
-    if (gy >= nr || gx >= nc) return;
     float oa[K::U], oh[K::U], ov[K::U], od[K::U];
 #pragma unroll
     for (int u = 0; u < K::U; u++) {
@@ -171,6 +176,7 @@ __global__ void __launch_bounds__(kNsThreads, 2)
                 pa[u] = oa[u]; ph[u] = oh[u]; pv[u] = ov[u]; pd[u] = od[u];
             }
     }
+    }   // row groups
 }
 
 // ================================================================================================== inverse
@@ -316,13 +322,21 @@ static int launch_ns_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
     using K = NsFwdCfg<HLEN>;
     static PerDeviceOnce once;
     if (once.first()) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)K::smem(K::MAXRG)));
     }
-    dim3 grid(idiv_up(half_up(Nc), K::TW), idiv_up(half_up(Nr), K::TH), batch);
+    // row groups per CTA, as in launch_ns_inv: amortise the staged halo while the grid still fills the GPU several times
+    int rg = K::MAXRG;
+    if (const char* e = getenv("PDWT_NS_RG")) rg = atoi(e);
+    else
+        while (rg > 1 && (long long)idiv_up(half_up(Nc), K::TW) * idiv_up(half_up(Nr), K::TH * rg) * batch < 3LL * 2 * 148) rg >>= 1;
+    if (rg < 1) rg = 1;
+    if (rg > K::MAXRG) rg = K::MAXRG;
+    dim3 grid(idiv_up(half_up(Nc), K::TW), idiv_up(half_up(Nr), K::TH * rg), batch);
     if (grid.y > 65535u) return 0;
     PDWT_PROF(prof_tag("k_nonsep_fwd_tiled", Nr, Nc), s);
-    PDWT_CUDA(launch_pdl(k_nonsep_fwd_tiled<HLEN>, grid, kNsThreads, K::SMEM, s, t, (const float*)img.p, img.stride, A.p,
-                         A.stride, H.p, V.p, D.p, H.stride, Nr, Nc));
+    PDWT_CUDA(launch_pdl(k_nonsep_fwd_tiled<HLEN>, grid, kNsThreads, K::smem(rg), s, t, (const float*)img.p, img.stride, A.p,
+                         A.stride, H.p, V.p, D.p, H.stride, Nr, Nc, rg));
     PDWT_LAUNCH_CHECK();
     return 1;
 }
