@@ -334,3 +334,40 @@ def test_norms_after_threshold_come_from_the_threshold_launch(monkeypatch):
             s1 = np.atleast_1d(W.norm1())
             assert L.pdwt_launch_count() > before
             assert np.all(np.abs(s1 - f1 / np.float32(1.5)) <= 1e-5 * np.abs(f1))
+
+
+def test_norm_publication_repeats_and_unaligned_planes():
+    """the norms travel to the host as tagged 8-byte words written by the last block of the launch (HostPublish,
+    pdwt_common.cuh): many launches in a row on one object (tickets and scratch re-armed by the kernel itself), thresholds
+    back to back, and odd-sized batched planes (plane strides that are not multiples of 4 floats: scalar heads and tails
+    of the flat tile walk) -- every value against the oracle at 1e-5, thresholded coefficients bit-exact"""
+    for shape, wname, levels, kw in (((5, 3, 37), "db2", 3, {"ndim": 1}), ((3, 33, 47), "db3", 2, {}),
+                                     ((2, 57, 64), "sym4", 2, {"do_swt": 1}), ((4096, 512), "db7", 3, {})):
+        x = rnd(shape, 77)
+        W = Wavelets(x, wname, levels, **kw)
+        planes = x if x.ndim == 3 else x[None]
+        Os = [oracle.Wavelets(p, wname, levels, **kw) for p in planes]
+        W.forward()
+        for O in Os:
+            O.forward()
+        ref1 = np.array([O.norm1() for O in Os], dtype=np.float64)
+        ref2 = np.array([O.norm2sq() for O in Os], dtype=np.float64)
+        for _ in range(25):   # uncached reductions, alternating modes
+            n1, n2 = np.atleast_1d(W.norm1()), np.atleast_1d(W.norm2sq())
+            assert np.all(np.abs(n1 - ref1) <= 1e-5 * np.abs(ref1)) and np.all(np.abs(n2 - ref2) <= 1e-5 * np.abs(ref2)), shape
+        for it in range(6):   # thresholds back to back: only the last one's sums may be read
+            W.soft_threshold(3.0, it & 1, 1)
+            W.hard_threshold(2.0, 0, 0)
+            for O in Os:
+                O.soft_threshold(3.0, it & 1, 1)
+                O.hard_threshold(2.0, 0, 0)
+            ref1 = np.array([O.norm1() for O in Os], dtype=np.float64)
+            ref2 = np.array([O.norm2sq() for O in Os], dtype=np.float64)
+            n1, n2 = np.atleast_1d(W.norm1()), np.atleast_1d(W.norm2sq())
+            assert np.all(np.abs(n1 - ref1) <= 1e-5 * np.abs(ref1) + 1e-30), (shape, it)
+            assert np.all(np.abs(n2 - ref2) <= 1e-5 * np.abs(ref2) + 1e-30), (shape, it)
+        for i in range(W.ncoeffs):
+            c = W.get_coeff(i)
+            c = c if x.ndim == 3 else c[None]
+            for b, O in enumerate(Os):
+                assert bitexact(c[b].reshape(-1), np.asarray(O.get_coeff(i)).reshape(-1)), (shape, i, b)
