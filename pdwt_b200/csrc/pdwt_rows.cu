@@ -60,8 +60,19 @@ __global__ void __launch_bounds__(kRowThreads)
     const size_t row = blockIdx.y, pz = blockIdx.z;
     const float* x = img + pz * s_img + row * Nc;
     pdl_wait();
-    for (int u = tid; u < K::NS; u += kRowThreads)
-        rows_cp4(S + u, x + rows_clamp(fold_dec(2 * k0 - K::C + u, Nc), Nc - 1));
+    {   // staged columns [u_lo, u_hi) lie inside the row: only the others pay for the fold
+        const int xs = 2 * k0 - K::C;
+        const int u_lo = max(0, -xs), u_hi = min(K::NS, Nc - xs);
+#pragma unroll
+        for (int k = 0; k < (K::NS + kRowThreads - 1) / kRowThreads; k++) {
+            const int u = tid + kRowThreads * k;
+            if (u < K::NS) {
+                int xi = xs + u;
+                if (u < u_lo || u >= u_hi) xi = rows_clamp(fold_dec(xi, Nc), Nc - 1);
+                rows_cp4(S + u, x + xi);
+            }
+        }
+    }
     rows_cp_wait();
     __syncthreads();
     pdl_launch_dependents();
@@ -109,10 +120,19 @@ __global__ void __launch_bounds__(kRowThreads)
     const float* p1 = t1 + pz * s_1 + row * n;
     const float* p2 = t2 + pz * s_2 + row * n;
     pdl_wait();
-    for (int u = tid; u < K::NS; u += kRowThreads) {
-        const int x = rows_wrap1(m0 - K::CC + u, n);
-        rows_cp4(S1 + u, p1 + x);
-        rows_cp4(S2 + u, p2 + x);
+    {
+        const int xs = m0 - K::CC;
+        const int u_lo = max(0, -xs), u_hi = min(K::NS, n - xs);   // no wrap needed inside [u_lo, u_hi)
+#pragma unroll
+        for (int k = 0; k < (K::NS + kRowThreads - 1) / kRowThreads; k++) {
+            const int u = tid + kRowThreads * k;
+            if (u < K::NS) {
+                int x = xs + u;
+                if (u < u_lo || u >= u_hi) x = rows_wrap1(x, n);
+                rows_cp4(S1 + u, p1 + x);
+                rows_cp4(S2 + u, p2 + x);
+            }
+        }
     }
     rows_cp_wait();
     __syncthreads();
@@ -177,10 +197,15 @@ __global__ void __launch_bounds__(kRowThreads)
     const float* p1 = in1 + pz * s_1 + row * Nc;
     const float* p2 = INV ? in2 + pz * s_2 + row * Nc : nullptr;
     pdl_wait();
-    for (int u = tid; u < ns; u += kRowThreads) {
-        const int x = rows_wrap1(g0 - c + u, Nc);
-        rows_cp4(S1 + u, p1 + x);
-        if (INV) rows_cp4(S2 + u, p2 + x);
+    {
+        const int xs = g0 - c;
+        const int u_lo = max(0, -xs), u_hi = min(ns, Nc - xs);   // no wrap needed inside [u_lo, u_hi)
+        for (int u = tid; u < ns; u += kRowThreads) {
+            int x = xs + u;
+            if (u < u_lo || u >= u_hi) x = rows_wrap1(x, Nc);
+            rows_cp4(S1 + u, p1 + x);
+            if (INV) rows_cp4(S2 + u, p2 + x);
+        }
     }
     rows_cp_wait();
     __syncthreads();
