@@ -193,12 +193,14 @@ struct NsInvCfg {
     static constexpr int NW = WIN + P - 1;            // window columns of a thread (both positions); even
     static_assert(P == 2 && (PITCH % 2) == 0 && (NW % 2) == 0, "128-bit window loads");
     static constexpr int MAXRG = 4;                   // a CTA stages once for up to MAXRG groups of THC coefficient rows
+    // resident CTAs per SM the register allocation aims for: 3 (80 registers) where ptxas gets there without spilling
+    static constexpr int MINB = (HLEN == 12 || HLEN == 16 || HLEN == 20) ? 2 : 3;
     // (A,H) tile + (V,D) tile as float2, then K'[ey][ex][jy][jx] as float4
     static constexpr size_t smem(int rg) { return sizeof(float2) * 2 * (size_t)(rg * THC + WIN - 1) * PITCH + sizeof(float4) * 4 * H2 * H2; }
 };
 
 template <int HLEN>
-__global__ void __launch_bounds__(kNsThreads, 2)
+__global__ void __launch_bounds__(kNsThreads, NsInvCfg<HLEN>::MINB)
     k_nonsep_inv_tiled(const __grid_constant__ Taps t, float* __restrict__ img, size_t s_img, const float* __restrict__ A,
                        size_t s_a, const float* __restrict__ H, const float* __restrict__ V, const float* __restrict__ D,
                        size_t s_d, int Nr, int Nc, int Nr2, int Nc2,   // Nr x Nc coefficients -> Nr2 x Nc2 pixels
