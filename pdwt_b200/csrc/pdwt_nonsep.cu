@@ -196,12 +196,20 @@ struct NsInvCfg {
     // resident CTAs per SM the register allocation aims for: 3 (80 registers) where ptxas gets there without spilling
     static constexpr int MINB = (HLEN == 12 || HLEN == 16 || HLEN == 20) ? 2 : 3;
     // (A,H) tile + (V,D) tile as float2, then K'[ey][ex][jy][jx] as float4
-    static constexpr size_t smem(int rg) { return sizeof(float2) * 2 * (size_t)(rg * THC + WIN - 1) * PITCH + sizeof(float4) * 4 * H2 * H2; }
+    static constexpr size_t smem(int rg) { return sizeof(float2) * 2 * (size_t)(rg * THC + WIN - 1) * PITCH; }
+};
+// The synthesis products K'[ey][ex][jy][jx] = (LL', LH', HL', HH') travel as a KERNEL PARAMETER (constant bank): the
+// inner loop fetches them through the uniform datapath (LDCU) into uniform registers that FFMA2 reads directly, instead
+// of 28 broadcast shared-memory loads per window row that competed with the window loads for the one shared-memory pipe
+// of the SM (the kernel was co-limited by it: 60 wavefronts against 224 FP32-pipe cycles per warp and window row).
+template <int HLEN>
+struct NsInvK {
+    float4 k[2][2][HLEN / 2][HLEN / 2];
 };
 
 template <int HLEN>
 __global__ void __launch_bounds__(kNsThreads, NsInvCfg<HLEN>::MINB)
-    k_nonsep_inv_tiled(const __grid_constant__ Taps t, float* __restrict__ img, size_t s_img, const float* __restrict__ A,
+    k_nonsep_inv_tiled(const __grid_constant__ NsInvK<HLEN> kt, float* __restrict__ img, size_t s_img, const float* __restrict__ A,
                        size_t s_a, const float* __restrict__ H, const float* __restrict__ V, const float* __restrict__ D,
                        size_t s_d, int Nr, int Nc, int Nr2, int Nc2,   // Nr x Nc coefficients -> Nr2 x Nc2 pixels
                        int rg)                                          // groups of THC coefficient rows per CTA
@@ -212,19 +220,9 @@ __global__ void __launch_bounds__(kNsThreads, NsInvCfg<HLEN>::MINB)
     const int inr = rg * K::THC + WIN - 1;          // staged rows: the halo is paid once for rg row groups
     float2* S_ah = reinterpret_cast<float2*>(smem);
     float2* S_vd = S_ah + inr * K::PITCH;
-    float4* S_k = reinterpret_cast<float4*>(S_vd + inr * K::PITCH);   // [ey][ex][jy][jx] -> (LL', LH', HL', HH')
     const int tid = threadIdx.x;
     const int cx0 = blockIdx.x * K::TWC, cy0 = blockIdx.y * (K::THC * rg);
 
-    // synthesis products per output parity e (0 = even output index): tap j multiplies I?[hlen-1-(2j+off_e)] with
-    // off_e = e ? SHIFT : 1-SHIFT (nonseparable.cu:186-204)
-    for (int i = tid; i < 4 * H2 * H2; i += kNsThreads) {
-        const int jx = i % H2, jy = (i / H2) % H2, ex = (i / (H2 * H2)) & 1, ey = i / (2 * H2 * H2);
-        const int oy = ey ? SHIFT : 1 - SHIFT, ox = ex ? SHIFT : 1 - SHIFT;
-        const float ly = t.IL[HLEN - 1 - (2 * jy + oy)], hy = t.IH[HLEN - 1 - (2 * jy + oy)];
-        const float lx = t.IL[HLEN - 1 - (2 * jx + ox)], hx = t.IH[HLEN - 1 - (2 * jx + ox)];
-        S_k[i] = make_float4(__fmul_rn(ly, lx), __fmul_rn(ly, hx), __fmul_rn(hy, lx), __fmul_rn(hy, hx));
-    }
     pdl_wait();
     const float* pa = A + (size_t)blockIdx.z * s_a;
     const float* ph = H + (size_t)blockIdx.z * s_d;
@@ -286,7 +284,7 @@ __global__ void __launch_bounds__(kNsThreads, NsInvCfg<HLEN>::MINB)
             for (int ex = 0; ex < 2; ex++)
 #pragma unroll
                 for (int jx = 0; jx < H2; jx++) {   // ascending (jy, jx) for every output: the reference's order
-                    const float4 k = S_k[((ey * 2 + ex) * H2 + jy) * H2 + jx];
+                    const float4 k = kt.k[ey][ex][jy][jx];   // jy uniform, the rest compile-time
                     const u64 k01 = ns_pack2(k.x, k.y), k23 = ns_pack2(k.z, k.w);
 #pragma unroll
                     for (int p = 0; p < K::P; p++) {
@@ -364,8 +362,22 @@ static int launch_ns_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
     if (rg > K::MAXRG) rg = K::MAXRG;
     dim3 grid(idiv_up(Nc, K::TWC), idiv_up(Nr, K::THC * rg), batch);
     if (grid.y > 65535u) return 0;
+    // synthesis products per output parity e (0 = even output index): tap j multiplies I?[hlen-1-(2j+off_e)] with
+    // off_e = e ? SHIFT : 1-SHIFT (nonseparable.cu:186-204); each product is ONE fp32 multiplication,
+    // rounded to nearest, exactly what the reference's w_outer leaves in its filter arrays (nonseparable.cu:16-24)
+    NsInvK<HLEN> kt;
+    for (int ey = 0; ey < 2; ey++)
+        for (int ex = 0; ex < 2; ex++)
+            for (int jy = 0; jy < K::H2; jy++)
+                for (int jx = 0; jx < K::H2; jx++) {
+                    const int oy = ey ? K::SHIFT : 1 - K::SHIFT, ox = ex ? K::SHIFT : 1 - K::SHIFT;
+                    const volatile float ly = t.IL[HLEN - 1 - (2 * jy + oy)], hy = t.IH[HLEN - 1 - (2 * jy + oy)];
+                    const volatile float lx = t.IL[HLEN - 1 - (2 * jx + ox)], hx = t.IH[HLEN - 1 - (2 * jx + ox)];
+                    volatile float ll = ly * lx, lh = ly * hx, hl = hy * lx, hh = hy * hx;   // no contraction, no excess precision
+                    kt.k[ey][ex][jy][jx] = make_float4(ll, lh, hl, hh);
+                }
     PDWT_PROF(prof_tag("k_nonsep_inv_tiled", Nr2, Nc2), s);
-    PDWT_CUDA(launch_pdl(k_nonsep_inv_tiled<HLEN>, grid, kNsThreads, K::smem(rg), s, t, img.p, img.stride, (const float*)A.p,
+    PDWT_CUDA(launch_pdl(k_nonsep_inv_tiled<HLEN>, grid, kNsThreads, K::smem(rg), s, kt, img.p, img.stride, (const float*)A.p,
                          A.stride, (const float*)H.p, (const float*)V.p, (const float*)D.p, H.stride, Nr, Nc, Nr2, Nc2, rg));
     PDWT_LAUNCH_CHECK();
     return 1;
