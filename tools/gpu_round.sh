@@ -1,7 +1,7 @@
 #!/bin/bash
 # one gpurun call that produces everything profiles/ holds for a round: parity tests, smoke, both bench arms, the batched
 # workloads, the ncu launch list of the bench command and one ncu --set full capture of the six level kernels
-TAG=${1:-r01g}
+TAG=${1:-r02a}
 O=gpurun_out/$TAG; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader > $O/smi.txt 2>&1; nproc >> $O/smi.txt
 ( time python -m pytest tests -m gpu -x -q ) > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
@@ -16,4 +16,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-cpu > $O/bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_ -s 12 -c 6 -o $O/ncu_c2 python tools/prof_fwdinv.py 3 > $O/ncu_c2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_ -s 6 -c 6 -o $O/ncu_b16 python tools/prof_batch.py > $O/ncu_b16.log 2>&1
+# the other kernel families: reductions / thresholds, SWT and non-separable level kernels
+ncu --set full --clock-control none --import-source on -k regex:"k_reduce|k_threshold" -c 6 -o $O/ncu_elem python tools/prof_elem.py > $O/ncu_elem.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_swt|k_nonsep" -s 12 -c 12 -o $O/ncu_c3c4 python tools/prof_c3c4.py > $O/ncu_c3c4.log 2>&1
+for r in c2 b16 elem c3c4; do ncu -i $O/ncu_$r.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_summary.py > $O/ncu_${r}_summary.txt; done
 tail -3 $O/pytest_gpu.log; tail -2 $O/smoke.log; cut -c1-300 $O/bench_ref.json; cut -c1-300 $O/bench_ours.json; cat $O/sequence.txt | head -5
