@@ -18,6 +18,6 @@ ncu --set full --clock-control none --import-source on -k regex:k_ -s 12 -c 6 -o
 ncu --set full --clock-control none --import-source on -k regex:k_ -s 6 -c 6 -o $O/ncu_b16 python tools/prof_batch.py > $O/ncu_b16.log 2>&1
 # the other kernel families: reductions / thresholds, SWT and non-separable level kernels
 ncu --set full --clock-control none --import-source on -k regex:"k_reduce|k_threshold" -c 6 -o $O/ncu_elem python tools/prof_elem.py > $O/ncu_elem.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_swt|k_nonsep" -s 12 -c 12 -o $O/ncu_c3c4 python tools/prof_c3c4.py > $O/ncu_c3c4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_swt|k_nonsep" -s 8 -c 16 -o $O/ncu_c3c4 python tools/prof_c3c4.py > $O/ncu_c3c4.log 2>&1
 for r in c2 b16 elem c3c4; do ncu -i $O/ncu_$r.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_summary.py > $O/ncu_${r}_summary.txt; done
 tail -3 $O/pytest_gpu.log; tail -2 $O/smoke.log; cut -c1-300 $O/bench_ref.json; cut -c1-300 $O/bench_ours.json; cat $O/sequence.txt | head -5
