@@ -17,6 +17,8 @@
 // shared memory with __fmul_rn.  Every output is the reference's chain: from 0, taps in (jy, jx) lexicographic order, one
 // fmaf each (fma.rn.f32x2 = two IEEE fmaf); the inverse adds ((ra + rh) + rv) + rd (nonseparable.cu:222-223).
 // Any plane size (the periodic / odd-size folds of nonseparable.cu:139-152 and 205-214 are applied while staging).
+#include <type_traits>
+
 #include "pdwt_common.cuh"
 
 namespace pdwt {
@@ -70,9 +72,15 @@ struct NsFwdCfg {
     __host__ __device__ static constexpr int slot(int u) { return ((((u >> 2) & 1) * HALF + (u >> 3)) << 2) + (u & 3); }
 };
 
+// KC (opt-in, PDWT_NS_FWD_CONST=1; compiled and inspected, NOT yet measured on a GPU): the filter table arrives as a
+// kernel parameter and is read through the uniform datapath like the inverse's (see NsInvK) instead of from shared memory.
 template <int HLEN>
+struct NsFwdK {
+    float4 k[HLEN][HLEN];   // [jy][jx] -> (LL, LH, HL, HH)
+};
+template <int HLEN, bool KC>
 __global__ void __launch_bounds__(kNsThreads, 2)
-    k_nonsep_fwd_tiled(const __grid_constant__ Taps t, const float* __restrict__ img, size_t s_img, float* __restrict__ A,
+    k_nonsep_fwd_tiled(const __grid_constant__ std::conditional_t<KC, NsFwdK<HLEN>, Taps> t, const float* __restrict__ img, size_t s_img, float* __restrict__ A,
                        size_t s_a, float* __restrict__ H, float* __restrict__ V, float* __restrict__ D, size_t s_d, int Nr,
                        int Nc, int rg)   // rg: groups of TH output rows per CTA
 {
@@ -87,10 +95,12 @@ __global__ void __launch_bounds__(kNsThreads, 2)
     img += (size_t)blockIdx.z * s_img;
 
     // the four 2-D filters in accumulation order: tap (jy, jx) multiplies K[hlen-1-jy][hlen-1-jx] (nonseparable.cu:155-160)
-    for (int i = tid; i < HLEN * HLEN; i += kNsThreads) {
-        const int jy = i / HLEN, jx = i - jy * HLEN;
-        const float ly = t.L[HLEN - 1 - jy], hy = t.H[HLEN - 1 - jy], lx = t.L[HLEN - 1 - jx], hx = t.H[HLEN - 1 - jx];
-        S_k[i] = make_float4(__fmul_rn(ly, lx), __fmul_rn(ly, hx), __fmul_rn(hy, lx), __fmul_rn(hy, hx));
+    if constexpr (!KC) {
+        for (int i = tid; i < HLEN * HLEN; i += kNsThreads) {
+            const int jy = i / HLEN, jx = i - jy * HLEN;
+            const float ly = t.L[HLEN - 1 - jy], hy = t.H[HLEN - 1 - jy], lx = t.L[HLEN - 1 - jx], hx = t.H[HLEN - 1 - jx];
+            S_k[i] = make_float4(__fmul_rn(ly, lx), __fmul_rn(ly, hx), __fmul_rn(hy, lx), __fmul_rn(hy, hx));
+        }
     }
     pdl_wait();
     // input tile with the reference's fold (periodic; odd sizes repeat the last sample), nonseparable.cu:139-152
@@ -141,7 +151,9 @@ __global__ void __launch_bounds__(kNsThreads, 2)
         const float4* kp = S_k + jy * HLEN;
 #pragma unroll
         for (int jx = 0; jx < HLEN; jx++) {
-            const float4 k = kp[jx];
+            float4 k;
+            if constexpr (KC) k = t.k[jy][jx];   // jy uniform, jx compile-time
+            else k = kp[jx];
             const u64 kah = ns_pack2(k.x, k.y), kvd = ns_pack2(k.z, k.w);
 #pragma unroll
             for (int u = 0; u < K::U; u++) {
@@ -322,7 +334,9 @@ static int launch_ns_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
     using K = NsFwdCfg<HLEN>;
     static PerDeviceOnce once;
     if (once.first()) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)K::smem(K::MAXRG)));
+        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)K::smem(K::MAXRG)));
     }
     // row groups per CTA, as in launch_ns_inv: amortise the staged halo while the grid still fills the GPU several times
@@ -335,8 +349,22 @@ static int launch_ns_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
     dim3 grid(idiv_up(half_up(Nc), K::TW), idiv_up(half_up(Nr), K::TH * rg), batch);
     if (grid.y > 65535u) return 0;
     PDWT_PROF(prof_tag("k_nonsep_fwd_tiled", Nr, Nc), s);
-    PDWT_CUDA(launch_pdl(k_nonsep_fwd_tiled<HLEN>, grid, kNsThreads, K::smem(rg), s, t, (const float*)img.p, img.stride, A.p,
-                         A.stride, H.p, V.p, D.p, H.stride, Nr, Nc, rg));
+    static const bool kconst = []() { const char* e = getenv("PDWT_NS_FWD_CONST"); return e && atoi(e) != 0; }();
+    if (kconst) {   // opt-in: the filter table as a kernel parameter (same products: one fp32 multiplication each)
+        NsFwdK<HLEN> kt;
+        for (int jy = 0; jy < HLEN; jy++)
+            for (int jx = 0; jx < HLEN; jx++) {
+                const volatile float ly = t.L[HLEN - 1 - jy], hy = t.H[HLEN - 1 - jy];
+                const volatile float lx = t.L[HLEN - 1 - jx], hx = t.H[HLEN - 1 - jx];
+                volatile float ll = ly * lx, lh = ly * hx, hl = hy * lx, hh = hy * hx;
+                kt.k[jy][jx] = make_float4(ll, lh, hl, hh);
+            }
+        PDWT_CUDA(launch_pdl(k_nonsep_fwd_tiled<HLEN, true>, grid, kNsThreads, K::smem(rg), s, kt, (const float*)img.p,
+                             img.stride, A.p, A.stride, H.p, V.p, D.p, H.stride, Nr, Nc, rg));
+    } else {
+        PDWT_CUDA(launch_pdl(k_nonsep_fwd_tiled<HLEN, false>, grid, kNsThreads, K::smem(rg), s, t, (const float*)img.p,
+                             img.stride, A.p, A.stride, H.p, V.p, D.p, H.stride, Nr, Nc, rg));
+    }
     PDWT_LAUNCH_CHECK();
     return 1;
 }
