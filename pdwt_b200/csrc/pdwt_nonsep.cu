@@ -72,7 +72,7 @@ struct NsFwdCfg {
     __host__ __device__ static constexpr int slot(int u) { return ((((u >> 2) & 1) * HALF + (u >> 3)) << 2) + (u & 3); }
 };
 
-// KC (opt-in, PDWT_NS_FWD_CONST=1; compiled and inspected, NOT yet measured on a GPU): the filter table arrives as a
+// KC (opt-in, PDWT_NS_FWD_CONST=1; GPU parity bit-exact, not yet timed against the default side by side): the filter table arrives as a
 // kernel parameter and is read through the uniform datapath like the inverse's (see NsInvK) instead of from shared memory.
 template <int HLEN>
 struct NsFwdK {
