@@ -211,6 +211,7 @@ struct FwdParams {
     int ncg, nrc;            // column groups (NCW strips each), row chunks; grid = ncg * nrc * batch CTAs
     int use_tm;
     int pdl_early;           // PDWT_PDL=1: let the next kernel's CTAs in as soon as this one has started
+    unsigned poll_ns;        // producer: sleep between two rounds of polling that found no free ring slot
 };
 
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm, int x, int y, int z, unsigned bar)
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
                 }
             }
             TL(2, lane == 0 && next[0] == 1 && remaining == nstrips * (nss - 1));
-            if (!any) __nanosleep(40);
+            if (!any) __nanosleep(p.poll_ns);
         }
 #ifdef PDWT_EXPERIMENTS
         if (lane == 0 && blockIdx.x < 1024) {
@@ -368,10 +369,14 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
     const unsigned my_ring = ring_s + warp * NSS * G::SSB;
     const unsigned my_bar = bar_s + 16 * warp * NSS;
 
-    // pending output rows: slot (y mod H2); pairs (A,V) and (H,D) per owned column
-    u64 aLV[H2][NC], aHD[H2][NC];
+    // pending output rows: acc[pp] belongs to the output row that is pp row pairs back; pairs (A,V) and (H,D) per column.
+    // The file SHIFTS by one slot per row pair, and the shift rides on the second row's FFMA2s (destination slot pp+1,
+    // addend slot pp), so every register index is static with a loop body of ONE row pair: the code stays a few KB
+    // instead of the 88 KB of a body unrolled over hlen rows (instruction-fetch stalls were 13 % of the warp time of
+    // the batched level-1 kernel, profiles/r01m_ncu_full_summary.txt).
+    u64 aLV[H2 + 1][NC], aHD[H2 + 1][NC];
 #pragma unroll
-    for (int s = 0; s < H2; s++)
+    for (int s = 0; s <= H2; s++)
 #pragma unroll
         for (int c = 0; c < NC; c++) aLV[s][c] = aHD[s][c] = 0ull;
 
@@ -385,10 +390,8 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
     // this lane's window inside a staged row, as a generic pointer (plain loads keep their order w.r.t. the barriers)
     const char* lane_ring = static_cast<const char*>(__cvta_shared_to_generic(my_ring)) + 2 * NC * lane * 4;
 
-    // one input row: row pass on the lane's window, then the column pass scatters the fresh (lo, hi) pair
-    auto row_step = [&](const float (&xv)[G::NV * 4], const int sb, const int r) {
-        // row pass, w_kern_forward_pass1 (separable.cu:91-131): (lo, hi)[c] = sum_j x[2k - C + j] * (L, H)[hlen-1-j]
-        u64 lohi[NC];
+    // row pass, w_kern_forward_pass1 (separable.cu:91-131): (lo, hi)[c] = sum_j x[2k - C + j] * (L, H)[hlen-1-j]
+    auto row_pass = [&](const float (&xv)[G::NV * 4], u64 (&lohi)[NC]) {
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             u64 acc = 0ull;
@@ -398,19 +401,6 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
                 acc = ffma2(pack2(x, x), pack2(p.lh[j].x, p.lh[j].y), acc);
             }
             lohi[c] = acc;
-        }
-        // column pass, w_kern_forward_pass2 (separable.cu:135-176), scatter form: this input row is tap
-        // j = r + 2*pp of the output row that sits pp pairs back
-#pragma unroll
-        for (int pp = 0; pp < H2; pp++) {
-            const int j = r + 2 * pp;
-            const int sl = (sb - pp + H2) % H2;
-            const u64 kl = pack2(p.ly[j], p.ly[j]), kh = pack2(p.hy[j], p.hy[j]);
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                aLV[sl][c] = ffma2(lohi[c], kl, j == 0 ? 0ull : aLV[sl][c]);
-                aHD[sl][c] = ffma2(lohi[c], kh, j == 0 ? 0ull : aHD[sl][c]);
-            }
         }
     };
     auto load_row = [&](float (&xv)[G::NV * 4], const char* rowp) {
@@ -422,78 +412,75 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
         }
     };
 
-    // Software pipeline over row pairs: the first row of pair q+1 is pulled into registers at the end of pair q, and
-    // the "full" barrier of the next super-slot is probed while the last pair of the current one is computed.
-    int q = 0, pin = 0;                           // pair index, pair within its super-slot
+    int q = 0;                                    // row pair index within the chunk
     unsigned soff = 0, bar = my_bar, parity = 0;  // ring position (byte offset, full barrier, phase) of the super-slot
-    float xa[G::NV * 4], xb[G::NV * 4];
-    mbar_wait(bar, parity);
-    TL(3, threadIdx.x == 0);
-    load_row(xa, lane_ring);
-    for (;;) {
+    for (int k = 0; k < nss; k++) {
+        mbar_wait(bar, parity);
+        TL(3, threadIdx.x == 0 && k == 0);
+        const char* ssp = lane_ring + soff;
 #pragma unroll
-        for (int sb = 0; sb < H2; sb++) {  // body: H2 row pairs = hlen input rows; all register indices static
-            const char* rowa = lane_ring + soff + pin * (2 * G::WW * 4);
-            load_row(xb, rowa + G::WW * 4);
-            const bool more = q + 1 < npairs;
-            if (!more) pdl_launch_dependents();   // last row pair of this warp: the next kernel may start its prologue
-            const bool last_in_ss = pin == SR / 2 - 1;
-            unsigned nsoff = soff + G::SSB, nbar = bar + 16, nparity = parity;
-            if (nsoff == NSS * G::SSB) {
-                nsoff = 0;
-                nbar = my_bar;
-                nparity ^= 1;
-            }
-            unsigned ready = 1;
-            if (last_in_ss && more) ready = mbar_test(nbar, nparity);
-            row_step(xa, sb, 0);
-            const bool arrive_now = last_in_ss;
-            const unsigned cur_bar = bar;
-            auto advance = [&]() {   // ring position of the next pair, then its first row into xa
-                if (last_in_ss) {
-                    if (!ready) mbar_wait(nbar, nparity);
-                    soff = nsoff;
-                    bar = nbar;
-                    parity = nparity;
-                    pin = 0;
-                } else {
-                    pin++;
+        for (int pin = 0; pin < SR / 2; pin++) {
+            if (q < npairs) {                     // warp-uniform; false only in the tail of the chunk's last super-slot
+                float xa[G::NV * 4], xb[G::NV * 4];
+                load_row(xa, ssp + pin * (2 * G::WW * 4));
+                load_row(xb, ssp + pin * (2 * G::WW * 4) + G::WW * 4);
+                if (q + 1 >= npairs) pdl_launch_dependents();   // last row pair of this warp
+                u64 lohi0[NC], lohi1[NC];
+                row_pass(xa, lohi0);
+                // column pass, w_kern_forward_pass2 (separable.cu:135-176), scatter form: the first row of the pair is
+                // tap j = 2*pp of the output row pp pairs back (in place) ...
+#pragma unroll
+                for (int pp = 0; pp < H2; pp++) {
+                    const u64 kl = pack2(p.ly[2 * pp], p.ly[2 * pp]), kh = pack2(p.hy[2 * pp], p.hy[2 * pp]);
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        aLV[pp][c] = ffma2(lohi0[c], kl, pp == 0 ? 0ull : aLV[pp][c]);
+                        aHD[pp][c] = ffma2(lohi0[c], kh, pp == 0 ? 0ull : aHD[pp][c]);
+                    }
                 }
-                load_row(xa, lane_ring + soff + pin * (2 * G::WW * 4));
-            };
-            if (LOWOCC && more) advance();   // xa is consumed: prefetch now
-            row_step(xb, sb, 1);
-            if (arrive_now) {
-                // every lane has consumed all rows of this super-slot: hand it back to the producer
-                __syncwarp();
-                if (lane == 0) mbar_arrive(cur_bar + 8);
-            }
-            TL(4, q == 0 && threadIdx.x == 0);
-            TL(5, q == H2 - 1 && threadIdx.x == 0);
-            // the output row that received its last tap (j = hlen-1) in this pair
-            if (q >= H2 - 1) {
-                const int sl = (sb + 1) % H2;
-                if (col_ok) {
-                    float a0, v0, a1, v1, h0, d0, h1, d1;
-                    unpack2(aLV[sl][0], a0, v0);
-                    unpack2(aLV[sl][1], a1, v1);
-                    unpack2(aHD[sl][0], h0, d0);
-                    unpack2(aHD[sl][1], h1, d1);
-                    *reinterpret_cast<float2*>(oA) = make_float2(a0, a1);
-                    *reinterpret_cast<float2*>(oH) = make_float2(h0, h1);
-                    *reinterpret_cast<float2*>(oV) = make_float2(v0, v1);
-                    *reinterpret_cast<float2*>(oD) = make_float2(d0, d1);
+                row_pass(xb, lohi1);
+                // ... the second row is tap j = 2*pp + 1, and its result moves one slot up: next pair it is pp+1 back
+#pragma unroll
+                for (int pp = H2 - 1; pp >= 0; pp--) {
+                    const u64 kl = pack2(p.ly[2 * pp + 1], p.ly[2 * pp + 1]), kh = pack2(p.hy[2 * pp + 1], p.hy[2 * pp + 1]);
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        aLV[pp + 1][c] = ffma2(lohi1[c], kl, aLV[pp][c]);
+                        aHD[pp + 1][c] = ffma2(lohi1[c], kh, aHD[pp][c]);
+                    }
                 }
-                oA += p.nc; oH += p.nc; oV += p.nc; oD += p.nc;
+                TL(4, q == 0 && threadIdx.x == 0);
+                TL(5, q == H2 - 1 && threadIdx.x == 0);
+                // slot H2 received its last tap (j = hlen-1) in this pair
+                if (q >= H2 - 1) {
+                    if (col_ok) {
+                        float a0, v0, a1, v1, h0, d0, h1, d1;
+                        unpack2(aLV[H2][0], a0, v0);
+                        unpack2(aLV[H2][1], a1, v1);
+                        unpack2(aHD[H2][0], h0, d0);
+                        unpack2(aHD[H2][1], h1, d1);
+                        *reinterpret_cast<float2*>(oA) = make_float2(a0, a1);
+                        *reinterpret_cast<float2*>(oH) = make_float2(h0, h1);
+                        *reinterpret_cast<float2*>(oV) = make_float2(v0, v1);
+                        *reinterpret_cast<float2*>(oD) = make_float2(d0, d1);
+                    }
+                    oA += p.nc; oH += p.nc; oV += p.nc; oD += p.nc;
+                }
+                q++;
             }
-            if (!more) {
-                TL(6, threadIdx.x == 0);
-                return;
-            }
-            q++;
-            if (!LOWOCC) advance();
+        }
+        // every lane has consumed all rows of this super-slot: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8);
+        soff += G::SSB;
+        bar += 16;
+        if (soff == NSS * G::SSB) {
+            soff = 0;
+            bar = my_bar;
+            parity ^= 1;
         }
     }
+    TL(6, threadIdx.x == 0);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -585,6 +572,10 @@ static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plan
     }
     if (const char* e = getenv("PDWT_TH")) TH = atoi(e) > 0 ? atoi(e) : TH;
     p.TH = TH;
+    // a consumer needs > 1 us per super-slot and two more are staged behind it: the producer can afford to sleep
+    static const unsigned poll_ns = []() { const char* e = getenv("PDWT_POLL_NS"); return e ? (unsigned)atoi(e) : 200u; }();
+    p.poll_ns = poll_ns;
+    p.pdl_early = pdl_mode() == 1;
     p.nrc = idiv_up(nr, TH);
     const long long nctas = (long long)p.ncg * p.nrc * batch;
     if (nctas > 0x7fffffff) return 0;
