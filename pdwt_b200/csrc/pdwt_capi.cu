@@ -20,6 +20,7 @@ using namespace pdwt;
 struct pdwt_filters {
     Taps taps;
     char name[128];
+    pdwt::StreamPlans* plans;   // queues + device counters of the cross-level launches made with this handle (lazy)
 };
 
 namespace pdwt {
@@ -205,7 +206,12 @@ int pdwt_filters_create_custom(pdwt_filters** out, int hlen, const float* dec_lo
     return hlen;
 }
 
-void pdwt_filters_destroy(pdwt_filters* f) { free(f); }
+void pdwt_filters_destroy(pdwt_filters* f)
+{
+    if (!f) return;
+    if (f->plans) stream_plans_destroy(f->plans);
+    free(f);
+}
 int pdwt_filters_hlen(const pdwt_filters* f) { return f ? f->taps.hlen : PDWT_ERR_ARG; }
 int pdwt_filters_get(const pdwt_filters* f, float* dec_lo, float* dec_hi, float* rec_lo, float* rec_hi)
 {
@@ -272,6 +278,7 @@ struct Ctx {
     int batch;
     cudaStream_t s;
     size_t s_img, s_tmp;
+    StreamPlans* plans;
     Plane2 image() const { return Plane2{img, s_img}; }
     Plane2 scratch(size_t off = 0) const { return Plane2{tmp + off, s_tmp}; }
     Plane2 coeff(int k) const { return Plane2{c[k], pdwt_coeff_alloc_elems(w, k)}; }
@@ -298,25 +305,48 @@ int check_args(const pdwt_filters* f, float* d_image, float** d_coeffs, float* d
 inline bool lands_in_c0(int L, int l) { return ((L - 1 - l) & 1) == 0; }
 
 // ---- separable 2-D DWT --------------------------------------------------------------------------------------
+// Buffer plan of the fused families: the approximation of level l (1 <= l < L) lives in d_tmp at its own offset (the
+// levels never share storage, so the items of different levels may run concurrently inside one launch), the last one
+// in d_coeffs[0] as the API demands.  No D2D fix-up copies (separable.cu:234) and, unlike the reference, inverse() leaves
+// d_coeffs[0] intact.  d_tmp holds 2 Nr Nc floats per plane; the approximations need less than Nr Nc / 2.
+Plane2 approx_plane(const Ctx& x, int l)
+{
+    if (l == x.w.nlevels) return x.coeff(0);
+    size_t off = 0;
+    for (int i = 1; i < l; i++)
+        off += ((size_t)level_size(x.w.Nr, i, 0) * level_size(x.w.Nc, i, 0) + 63) & ~(size_t)63;
+    return x.scratch(off);
+}
+
 int fwd_sep_2d(const Ctx& x)
 {
     const int L = x.w.nlevels;
     int Nr = x.w.Nr, Nc = x.w.Nc;
     const int cap = path_cap();
-    if (fused_supports_hlen(x.t.hlen) && cap >= 1) {
-        Plane2 cur = x.image();
+    if (fused_supports_hlen(x.t.hlen) && cap >= 1 && L <= 32) {
+        StreamLevelIO io[32];
         for (int l = 0; l < L; l++) {
-            Plane2 dstA = lands_in_c0(L, l) ? x.coeff(0) : x.scratch();
+            io[l].img = l ? approx_plane(x, l) : x.image();
+            io[l].A = approx_plane(x, l + 1);
+            io[l].H = x.coeff(3 * l + 1);
+            io[l].V = x.coeff(3 * l + 2);
+            io[l].D = x.coeff(3 * l + 3);
+            io[l].Nr = level_size(x.w.Nr, l, 0);
+            io[l].Nc = level_size(x.w.Nc, l, 0);
+            io[l].a_reused = l + 1 < L;
+        }
+        for (int l = 0; l < L;) {
             int done = 0;
-            if (cap >= 2 && (long long)half_up(Nr) * half_up(Nc) * x.batch > small_level_px())
-                TRY(done = s_dwt2_fwd_level(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3),
-                                            Nr, Nc, x.batch, x.s));
-            if (!done)
-                TRY(f_dwt2_fwd_level(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr,
-                                     Nc, x.batch, x.s));
-            cur = dstA;
-            Nr = half_up(Nr);
-            Nc = half_up(Nc);
+            if (cap >= 2) {
+                int n = 0;   // consecutive levels large enough for the streaming family
+                while (l + n < L && (long long)half_up(io[l + n].Nr) * half_up(io[l + n].Nc) * x.batch > small_level_px()) n++;
+                if (n > 0) TRY(done = s_dwt2_fwd_levels(x.t, x.plans, io + l, n, x.batch, x.s));
+            }
+            if (!done) {
+                TRY(f_dwt2_fwd_level(x.t, io[l].img, io[l].A, io[l].H, io[l].V, io[l].D, io[l].Nr, io[l].Nc, x.batch, x.s));
+                done = 1;
+            }
+            l += done;
         }
         return PDWT_OK;
     }
@@ -337,21 +367,32 @@ int inv_sep_2d(const Ctx& x)
 {
     const int L = x.w.nlevels;
     const int cap = path_cap();
-    if (fused_supports_hlen(x.t.hlen) && cap >= 1) {
-        Plane2 cur = x.coeff(0);
-        bool cur_is_c0 = true;
-        for (int l = L - 1; l >= 0; l--) {
-            const int Mr = level_size(x.w.Nr, l, 0), Mc = level_size(x.w.Nc, l, 0);
-            Plane2 dst = (l == 0) ? x.image() : (cur_is_c0 ? x.scratch() : x.coeff(0));
+    if (fused_supports_hlen(x.t.hlen) && cap >= 1 && L <= 32) {
+        StreamLevelIO io[32];   // coarsest level first
+        for (int k = 0; k < L; k++) {
+            const int l = L - 1 - k;
+            io[k].A = approx_plane(x, l + 1);
+            io[k].H = x.coeff(3 * l + 1);
+            io[k].V = x.coeff(3 * l + 2);
+            io[k].D = x.coeff(3 * l + 3);
+            io[k].img = l ? approx_plane(x, l) : x.image();
+            io[k].Nr = level_size(x.w.Nr, l, 0);
+            io[k].Nc = level_size(x.w.Nc, l, 0);
+            io[k].a_reused = l > 0;
+        }
+        for (int k = 0; k < L;) {
             int done = 0;
-            if (cap >= 2 && (long long)half_up(Mr) * half_up(Mc) * x.batch > small_level_px())
-                TRY(done = s_dwt2_inv_level(x.t, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), dst,
-                                            half_up(Mr), half_up(Mc), Mr, Mc, x.batch, x.s));
-            if (!done)
-                TRY(f_dwt2_inv_level(x.t, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), dst,
-                                     half_up(Mr), half_up(Mc), Mr, Mc, x.batch, x.s));
-            cur = dst;
-            cur_is_c0 = !cur_is_c0;
+            if (cap >= 2) {
+                int n = 0;
+                while (k + n < L && (long long)half_up(io[k + n].Nr) * half_up(io[k + n].Nc) * x.batch > small_level_px()) n++;
+                if (n > 0) TRY(done = s_dwt2_inv_levels(x.t, x.plans, io + k, n, x.batch, x.s));
+            }
+            if (!done) {
+                TRY(f_dwt2_inv_level(x.t, io[k].A, io[k].H, io[k].V, io[k].D, io[k].img, half_up(io[k].Nr), half_up(io[k].Nc),
+                                     io[k].Nr, io[k].Nc, x.batch, x.s));
+                done = 1;
+            }
+            k += done;
         }
         return PDWT_OK;
     }
@@ -545,12 +586,23 @@ int inv_single(const Ctx& x, Family fam)
 
 const Taps kNoTaps = {};
 
+// the handle's plan cache, created on first use (the handle is `const` for the caller: the cache is an implementation detail)
+StreamPlans* plans_of(const pdwt_filters* f)
+{
+    if (!f) return nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    pdwt_filters* m = const_cast<pdwt_filters*>(f);
+    if (!m->plans) m->plans = stream_plans_create();
+    return m->plans;
+}
+
 }  // namespace
 
 #define MAKE_CTX(need_f)                                                                      \
     TRY(check_args(f, d_image, d_coeffs, d_tmp, winfos, batch, need_f));                      \
     Ctx x{(need_f) ? f->taps : kNoTaps, d_image, d_coeffs, d_tmp, winfos, batch, (cudaStream_t)stream, \
-          (size_t)winfos.Nr * winfos.Nc, 2 * (size_t)winfos.Nr * winfos.Nc}
+          (size_t)winfos.Nr * winfos.Nc, 2 * (size_t)winfos.Nr * winfos.Nc, plans_of(f)}
 
 extern "C" {
 

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "../../include/pdwt_b200.h"
 
 namespace pdwt {
@@ -94,23 +95,33 @@ const char* prof_tag(const char* base, int rows, int cols);  // "base[rows x col
 
 inline int idiv_up(int a, int b) { return (a + b - 1) / b; }
 
-// Function attributes (dynamic shared memory limits) are per DEVICE: `static PerDeviceOnce once; if (once.first()) {...}`
-// runs its body the first time the call site is reached on each device of a process that uses several.
+// Function attributes (dynamic shared memory limits) are per DEVICE: PDWT_ONCE_PER_DEVICE(call) runs `call` the first
+// time its call site is reached on each device of the process.  The body runs under the site's lock, and the device is
+// marked done only when the call has succeeded, so concurrent first launches from several host threads (one object per
+// thread) neither skip the attribute nor leave a failed call un-retried.
 struct PerDeviceOnce {
+    std::mutex mu;
     unsigned long long mask = 0;
-    int dev = 0;
-    bool first()
+    template <typename F>
+    cudaError_t run(F body, int* dev_out = nullptr)
     {
-        dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) {
-            dev = 0;
-            return true;
-        }
-        if ((mask >> dev) & 1ull) return false;
-        mask |= 1ull << dev;
-        return true;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev_out) *dev_out = dev;
+        std::lock_guard<std::mutex> g(mu);
+        if (dev >= 0 && dev < 64 && ((mask >> dev) & 1ull)) return cudaSuccess;
+        e = body();
+        if (e == cudaSuccess && dev >= 0 && dev < 64) mask |= 1ull << dev;
+        return e;
     }
 };
+#define PDWT_ONCE_PER_DEVICE(call)                                                    \
+    do {                                                                              \
+        static ::pdwt::PerDeviceOnce once__;                                          \
+        cudaError_t eo__ = once__.run([&]() -> cudaError_t { return (call); });       \
+        if (eo__ != cudaSuccess) return ::pdwt::note_cuda(eo__);                      \
+    } while (0)
 
 // level geometry of one plane
 inline int level_size(int N, int l, int do_swt)
@@ -160,11 +171,21 @@ int f_dwt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Pl
 int f_dwt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
                      int batch, cudaStream_t s);
 
-// ---- warp-streaming FFMA2 kernels, pdwt_stream.cu: same convention (1 = handled, 0 = shape not covered, < 0 = error)
-int s_dwt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
-                     cudaStream_t s);
-int s_dwt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
-                     int batch, cudaStream_t s);
+// ---- warp-streaming FFMA2 kernels, pdwt_stream.cu.  One call takes SEVERAL consecutive levels and serves them with one
+// launch (cross-level queue, see the file); `plans` caches the queues and their device counters (NULL: one level per call).
+struct StreamLevelIO {   // one level: image / approximation `img` (Nr x Nc)  <->  sub-bands A, H, V, D (Nr/2 x Nc/2)
+    Plane2 img, A, H, V, D;
+    int Nr, Nc;
+    int a_reused;        // forward: A is read again by a later kernel (keep it in L2); inverse: same for img
+};
+struct StreamPlans;
+StreamPlans* stream_plans_create();
+void stream_plans_destroy(StreamPlans* p);
+// forward: lv[0] is the finest level, lv[i+1].img == lv[i].A.  Returns how many LEADING levels were launched (0: the
+// first one's shape is not covered), < 0 on error.
+int s_dwt2_fwd_levels(const Taps& t, StreamPlans* plans, const StreamLevelIO* lv, int nlev, int batch, cudaStream_t s);
+// inverse: lv[0] is the coarsest level of the group, lv[i+1].A == lv[i].img.  Same return convention.
+int s_dwt2_inv_levels(const Taps& t, StreamPlans* plans, const StreamLevelIO* lv, int nlev, int batch, cudaStream_t s);
 
 // ---- fused SWT level kernels, pdwt_swt.cu: same convention; w_swt2_supported tells whether EVERY level 1..nlevels of a
 // transform can take them (the caller's buffer plan depends on it)

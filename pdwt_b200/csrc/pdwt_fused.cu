@@ -348,10 +348,7 @@ static int launch_fwd_t(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V,
                         cudaStream_t s)
 {
     using K = FwdCfg<HLEN, TW, TH>;
-    static PerDeviceOnce once;
-    if (once.first()) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_fwd2d<HLEN, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-    }
+    PDWT_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_fwd2d<HLEN, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
     dim3 grid(idiv_up(half_up(Nc), TW), idiv_up(half_up(Nr), TH), batch);
     PDWT_PROF(prof_tag("k_fwd2d", Nr, Nc), s);
     PDWT_CUDA(launch_pdl(k_fwd2d<HLEN, TW, TH>, grid, kFusedThreads, K::SMEM, s, t, (const float*)src.p, src.stride, A.p,
@@ -373,10 +370,7 @@ static int launch_inv_t(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, P
                         int batch, cudaStream_t s)
 {
     using K = InvCfg<HLEN, TWC, THC>;
-    static PerDeviceOnce once;
-    if (once.first()) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_inv2d<HLEN, TWC, THC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-    }
+    PDWT_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_inv2d<HLEN, TWC, THC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
     dim3 grid(idiv_up(nc, TWC), idiv_up(nr, THC), batch);
     PDWT_PROF(prof_tag("k_inv2d", Mr, Mc), s);
     PDWT_CUDA(launch_pdl(k_inv2d<HLEN, TWC, THC>, grid, kFusedThreads, K::SMEM, s, t, (const float*)A.p, A.stride,

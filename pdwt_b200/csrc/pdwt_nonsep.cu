@@ -332,13 +332,10 @@ static int launch_ns_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
                          cudaStream_t s)
 {
     using K = NsFwdCfg<HLEN>;
-    static PerDeviceOnce once;
-    if (once.first()) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)K::smem(K::MAXRG)));
-        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)K::smem(K::MAXRG)));
-    }
+    PDWT_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)K::smem(K::MAXRG)));
+    PDWT_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_nonsep_fwd_tiled<HLEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)K::smem(K::MAXRG)));
     // row groups per CTA, as in launch_ns_inv: amortise the staged halo while the grid still fills the GPU several times
     int rg = K::MAXRG;
     if (const char* e = getenv("PDWT_NS_RG")) rg = atoi(e);
@@ -375,11 +372,8 @@ static int launch_ns_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
 {
     using K = NsInvCfg<HLEN>;
     if (Nr < K::WIN || Nc < K::WIN) return 0;   // the single wrap must suffice
-    static PerDeviceOnce once;
-    if (once.first()) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_nonsep_inv_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)K::smem(K::MAXRG)));
-    }
+    PDWT_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_nonsep_inv_tiled<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)K::smem(K::MAXRG)));
     // Row groups per CTA: more groups amortise the staged halo (WIN - 1 rows) and the staging latency over more
     // arithmetic, as long as the grid still fills the GPU several times over (2 CTAs per SM are resident).
     int rg = K::MAXRG;

@@ -304,10 +304,7 @@ static int launch_rows_swt(const Taps& t, Plane2 in1, Plane2 in2, Plane2 out1, P
     PDWT_PROF(prof_tag(INV ? "k_rows_swt_inv" : "k_rows_swt_fwd", Nr, f), s);
 #define PDWT_ROWS_SWT_LAUNCH(FM)                                                                                          \
     do {                                                                                                                  \
-        static PerDeviceOnce once;                                                                                        \
-        if (once.first()) {                                                                                               \
-            PDWT_CUDA(cudaFuncSetAttribute(k_rows_swt<HLEN, FM, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
-        }                                                                                                                 \
+        PDWT_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_rows_swt<HLEN, FM, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
         PDWT_CUDA(launch_pdl(k_rows_swt<HLEN, FM, INV>, grid, kRowThreads, smem, s, t, (const float*)in1.p, in1.stride,  \
                              (const float*)in2.p, in2.stride, out1.p, out1.stride, out2.p, out2.stride, Nc, f, vec));    \
     } while (0)

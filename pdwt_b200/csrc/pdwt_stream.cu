@@ -30,6 +30,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <functional>
+#include <mutex>
+#include <queue>
+#include <vector>
+
 #include "pdwt_common.cuh"
 
 namespace pdwt {
@@ -197,19 +203,87 @@ struct FwdGeom {
     static_assert(SSB % 128 == 0 && WW <= 256 && SR % 2 == 0, "tensor-map box constraints");
 };
 
-template <int HLEN>
-struct FwdParams {
+// ---- cross-level execution (one launch per direction for all levels of a transform) --------------------------------
+// The reference queues one pair of kernels per level, each waiting for the previous one's last thread block
+// (separable.cu:179-209, 332-364), and every intermediate approximation makes a round trip through DRAM.  Here the work
+// items of ALL levels (and all planes of a batch) form ONE ordered queue served by one launch: a CTA draws a ticket,
+// looks its item up, and -- if the item reads an approximation produced inside the launch -- waits until the row chunks
+// it needs are complete (one counter per producing row chunk, bumped with a gpu-scope release by every finishing warp).
+// Items are ordered so that producers sit well ahead of their consumers in the queue (image-major, the small levels of
+// plane b interleaved with level 1 of plane b+lag), so the wait is normally over before it starts, the approximation is
+// still in the 126 MB L2 when it is read, and the latency-bound small levels overlap the bandwidth-bound level 1.
+// Tickets (not blockIdx) make this deadlock-free: every item with a smaller ticket is already running or done.
+// Counters are cumulative over launches (`epoch`), so nothing has to be zeroed between launches.
+constexpr int kMaxLv = 6;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_inc(unsigned* p)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+// Completion counters: one per block of 2^fr_shift output rows of a producing level and plane (nb blocks per plane; the
+// level's row count is a multiple of the block).  Every warp that finishes a chunk bumps the counters of the blocks it
+// covers; a block is complete for launch `epoch` at epoch * (warps per block).
+// wait (the whole warp, converged) until every block that intersects the periodic row range [r0, r0 + nrows) is
+// complete.  Each lane polls another block and the loop condition is a vote: a spin loop run by ONE lane makes ptxas
+// treat the rest of the kernel as possibly diverged (BSSY/BSYNC around every branch, WARPSYNC, the uniform datapath lost:
+// the level-1 inverse kernel went from 33 to 50 us).
+__device__ __forceinline__ void wait_blocks(const unsigned* flags, int fr_shift, int nb, unsigned target, int r0, int nrows)
+{
+    const int lane = threadIdx.x & 31;
+    const int vb0 = r0 >> fr_shift, vb1 = (r0 + nrows - 1) >> fr_shift;   // arithmetic shift = floor for rows < 0
+    for (;;) {
+        bool ok = true;
+        for (int base = vb0; base <= vb1; base += 32) {
+            const int i = base + lane;
+            int j = i % nb;
+            j += (j < 0) ? nb : 0;
+            if (i <= vb1) ok = ok && (int)(ld_acquire_u32(flags + j) - target) >= 0;
+        }
+        if (__all_sync(0xffffffffu, ok)) break;
+        __nanosleep(100);
+    }
+}
+// this warp's share of output rows [y0, y0 + ny) is complete and stored: release it
+__device__ __forceinline__ void signal_blocks(unsigned* flags, int fr_shift, int y0, int ny)
+{
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    const int b0 = y0 >> fr_shift, b1 = (y0 + ny - 1) >> fr_shift;
+    for (int base = b0; base <= b1; base += 32)
+        if (base + lane <= b1) red_release_inc(flags + base + lane);
+}
+
+struct alignas(64) FwdLevel {
     CUtensorMap tm;   // (Nc, Nr, batch) fp32 tensor over the source planes, box (WW, SR, 1); valid iff use_tm
-    float2 lh[HLEN];  // (L[hlen-1-j], H[hlen-1-j]): row-pass tap pairs in the reference's accumulation order
-    float ly[HLEN];   // L[hlen-1-j]
-    float hy[HLEN];   // H[hlen-1-j]
     const float* src;
     float *A, *Hb, *V, *D;
     size_t s_src, s_a, s_d;  // plane strides (floats)
     int Nr, Nc, nr, nc;      // input and output plane sizes
-    int TH;                  // output rows per chunk
-    int ncg, nrc;            // column groups (NCW strips each), row chunks; grid = ncg * nrc * batch CTAs
+    int TH;                  // output rows per chunk (single-level launches; queue items carry their own rows)
+    int ncg, nrc;            // column groups (NCW strips each), row chunks
     int use_tm;
+    int nstrips;             // consumer warps per row = increments of a block's counter per launch
+    int flag_off;            // counters of this level: ctrl[flag_off + plane * nb + block]
+    int keep_a;              // A is read back by the next level of this launch: its items wait on these counters
+    int fr_shift, nb;        // counter block = 2^fr_shift output rows, nb blocks per plane
+};
+
+template <int HLEN>
+struct FwdParams {
+    FwdLevel lev[kMaxLv];
+    float2 lh[HLEN];  // (L[hlen-1-j], H[hlen-1-j]): row-pass tap pairs in the reference's accumulation order
+    float ly[HLEN];   // L[hlen-1-j]
+    float hy[HLEN];   // H[hlen-1-j]
+    const int4* items;       // (level | plane << 4, first output row, rows, column group) by ticket; NULL: one level, item = blockIdx
+    unsigned* ctrl;          // [0] ticket counter, row-chunk counters behind it (cumulative over launches)
+    unsigned ticket_base;    // tickets handed out by earlier launches
+    unsigned epoch;          // number of this launch (1, 2, ...): a chunk of level l is complete at epoch * nstrips(l)
     int pdl_early;           // PDWT_PDL=1: let the next kernel's CTAs in as soon as this one has started
     unsigned poll_ns;        // producer: sleep between two rounds of polling that found no free ring slot
 };
@@ -242,9 +316,7 @@ __device__ __forceinline__ void tl_stamp(int cta, int slot)
 #define TL(slot, cond) do { } while (0)
 #endif
 
-// LOWOCC: variant for grids that put at most 2 CTAs on an SM anyway (one image): it may use twice the registers, which
-// buys an earlier prefetch of the next pair's first row (its shared-memory latency hides behind the second row's FFMA2s
-// instead of sitting at the head of the next iteration; with the 4-CTA register budget that spills).
+// LOWOCC: variant for grids that put at most 2 CTAs on an SM anyway (one image): it may use more registers.
 template <int HLEN, bool LOWOCC>
 __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 14 ? 4 : 3))
     k_fwd2d_stream(const __grid_constant__ FwdParams<HLEN> p)
@@ -252,35 +324,65 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
     using G = FwdGeom<HLEN>;
     constexpr int H2 = G::H2, NC = G::NC, NSS = G::NSS, SR = G::SR, NCW = G::NCW;
     extern __shared__ unsigned char smem_raw[];
+    __shared__ int4 s_item;
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
-    const int item = blockIdx.x;
 
     const unsigned ring_s = (smem_u32(smem_raw) + 127u) & ~127u;   // tensor-map destinations are 128-byte aligned
     const unsigned bar_s = ring_s + NCW * NSS * G::SSB;            // full[w][s] at +16*(w*NSS+s), empty right behind it
-
-    const int cg = item % p.ncg, rest = item / p.ncg, rc = rest % p.nrc, plane = rest / p.nrc;
-    const int y0 = rc * p.TH;
-    const int ny = min(p.TH, p.nr - y0);
-    const int npairs = ny + H2 - 1;          // input row pairs this chunk consumes
-    const int nss = (2 * npairs + SR - 1) / SR;   // super-slots per consumer
-    const int vr0 = 2 * y0 - G::C;           // first input row (virtual: < 0 or >= Nr wraps around)
-    const int nstrips = min(NCW, (p.nc - cg * NCW * G::WO + G::WO - 1) / G::WO);   // strips of this CTA inside the image
     TL(0, threadIdx.x == 0);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NCW * NSS * 2; i++) mbar_init(bar_s + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (p.items) s_item = p.items[atomicAdd(p.ctrl, 1u) - p.ticket_base];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();   // the only block-wide barrier: after it the warps only meet through mbarriers
+    int level = 0, plane, y0, ny, cg;
+    if (p.items) {     // through warp reductions: their results live in uniform registers (CREDUX), see the inverse kernel
+        const int4 it = s_item;
+        const int lp = __reduce_max_sync(0xffffffffu, (unsigned)it.x);
+        level = lp & 15;
+        plane = lp >> 4;
+        y0 = __reduce_max_sync(0xffffffffu, (unsigned)it.y);
+        ny = __reduce_max_sync(0xffffffffu, (unsigned)it.z);
+        cg = __reduce_max_sync(0xffffffffu, (unsigned)it.w);
+    } else {
+        const int item = blockIdx.x, ncg0 = p.lev[0].ncg, nrc0 = p.lev[0].nrc;
+        cg = item % ncg0;
+        const int rest = item / ncg0;
+        plane = rest / nrc0;
+        y0 = (rest % nrc0) * p.lev[0].TH;
+        ny = min(p.lev[0].TH, p.lev[0].nr - y0);
+    }
+    const FwdLevel& L = p.lev[level];
+    const int Nr = L.Nr, Nc = L.Nc, nc_o = L.nc;
+    const int npairs = ny + H2 - 1;          // input row pairs this chunk consumes
+    const int nss = (2 * npairs + SR - 1) / SR;   // super-slots per consumer
+    const int vr0 = 2 * y0 - G::C;           // first input row (virtual: < 0 or >= Nr wraps around)
+    const int nstrips = min(NCW, (nc_o - cg * NCW * G::WO + G::WO - 1) / G::WO);   // strips of this CTA inside the image
     if (p.pdl_early) pdl_launch_dependents();
-    pdl_wait();        // the previous level's kernel (or whatever wrote `src`) has completed
+    pdl_wait();        // the previous kernel of the stream (whatever wrote the level-1 source) has completed
     TL(1, threadIdx.x == 0);
+#ifdef PDWT_EXPERIMENTS
+    if (threadIdx.x == 0 && blockIdx.x < 4096)   // slot 5: what this CTA worked on
+        g_timeline[blockIdx.x * 8 + 5] = (unsigned long long)level | ((unsigned long long)ny << 4) | ((unsigned long long)plane << 16) | ((unsigned long long)y0 << 32);
+#endif
 
     if (warp == NCW) {
         // ===================================================================================== producer warp
-        const float* src = p.src + (size_t)plane * p.s_src;
+        const float* src = L.src + (size_t)plane * L.s_src;
+        const CUtensorMap* tm = &L.tm;
+        const bool use_tm = L.use_tm != 0;
+        if (level > 0) {
+            // the source is the approximation written by level-1 items of this launch: wait for the row chunks this
+            // chunk reads (rows past its last pair inside the last super-slot are staged but never used)
+            const FwdLevel& P = p.lev[level - 1];
+            wait_blocks(p.ctrl + P.flag_off + plane * P.nb, P.fr_shift, P.nb, p.epoch * (unsigned)P.nstrips, vr0, 2 * npairs);
+            asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes -> the TMA engine's reads
+        }
+        TL(2, lane == 0);   // dependencies satisfied
         // super-slot k of strip w -> ring slot k % NSS
         auto issue = [&](const int k, const int w) {
             const int slot = k % NSS;
@@ -288,16 +390,16 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
             // rows needed from this super-slot all inside the image? (rows past the chunk's last pair may fall outside:
             // the tensor request zero-fills them and nobody reads them)
             const int last_needed = min(row0 + SR, vr0 + 2 * npairs) - 1;
-            const bool rows_in = row0 >= 0 && last_needed < p.Nr;
-            row0 += (row0 < 0) ? p.Nr : 0;
-            row0 -= (row0 >= p.Nr) ? p.Nr : 0;
+            const bool rows_in = row0 >= 0 && last_needed < Nr;
+            row0 += (row0 < 0) ? Nr : 0;
+            row0 -= (row0 >= Nr) ? Nr : 0;
             const unsigned full = bar_s + 16 * (w * NSS + slot);
             const int xs = 2 * (cg * NCW + w) * G::WO - G::AL;
             const unsigned dst = ring_s + (w * NSS + slot) * G::SSB;
-            if (p.use_tm && rows_in && xs >= 0 && xs + G::WW <= p.Nc) {
+            if (use_tm && rows_in && xs >= 0 && xs + G::WW <= Nc) {
                 if (elect_one()) {
                     mbar_expect_tx(full, G::SSB);
-                    tma_load_3d(dst, &p.tm, xs, vr0 + SR * k, plane, full);
+                    tma_load_3d(dst, tm, xs, vr0 + SR * k, plane, full);
                 }
             } else {
                 // periodic extension (separable.cu:114-121, even sizes): every lane copies 16-byte pieces with a
@@ -312,11 +414,11 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
                     const int i = lane + 32 * it;
                     const int r = i / CPR, c = i - r * CPR;
                     int row = row0 + r;
-                    row -= (row >= p.Nr) ? p.Nr : 0;
+                    row -= (row >= Nr) ? Nr : 0;
                     int x = xs + 4 * c;
-                    x += (x < 0) ? p.Nc : 0;
-                    x -= (x >= p.Nc) ? p.Nc : 0;
-                    g[it] = src + (size_t)row * p.Nc + x;
+                    x += (x < 0) ? Nc : 0;
+                    x -= (x >= Nc) ? Nc : 0;
+                    g[it] = src + (size_t)row * Nc + x;
                 }
 #pragma unroll
                 for (int it = 0; it < NIT; it++)
@@ -350,11 +452,10 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
                     }
                 }
             }
-            TL(2, lane == 0 && next[0] == 1 && remaining == nstrips * (nss - 1));
             if (!any) __nanosleep(p.poll_ns);
         }
 #ifdef PDWT_EXPERIMENTS
-        if (lane == 0 && blockIdx.x < 1024) {
+        if (lane == 0 && blockIdx.x < 4096) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             g_timeline[blockIdx.x * 8 + 7] = smid;   // slot 7: the SM this CTA ran on
@@ -381,12 +482,12 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
         for (int c = 0; c < NC; c++) aLV[s][c] = aHD[s][c] = 0ull;
 
     const int kcol = k0 + NC * lane;                 // first output column of this lane
-    const bool col_ok = kcol < p.nc;                 // nc is even, so the pair is in or out as a whole
-    const size_t o0 = (size_t)y0 * p.nc + kcol;
-    float* oA = p.A + (size_t)plane * p.s_a + o0;
-    float* oH = p.Hb + (size_t)plane * p.s_d + o0;
-    float* oV = p.V + (size_t)plane * p.s_d + o0;
-    float* oD = p.D + (size_t)plane * p.s_d + o0;
+    const bool col_ok = kcol < nc_o;                 // nc is even, so the pair is in or out as a whole
+    const size_t o0 = (size_t)y0 * nc_o + kcol;
+    float* oA = L.A + (size_t)plane * L.s_a + o0;
+    float* oH = L.Hb + (size_t)plane * L.s_d + o0;
+    float* oV = L.V + (size_t)plane * L.s_d + o0;
+    float* oD = L.D + (size_t)plane * L.s_d + o0;
     // this lane's window inside a staged row, as a generic pointer (plain loads keep their order w.r.t. the barriers)
     const char* lane_ring = static_cast<const char*>(__cvta_shared_to_generic(my_ring)) + 2 * NC * lane * 4;
 
@@ -450,7 +551,6 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
                     }
                 }
                 TL(4, q == 0 && threadIdx.x == 0);
-                TL(5, q == H2 - 1 && threadIdx.x == 0);
                 // slot H2 received its last tap (j = hlen-1) in this pair
                 if (q >= H2 - 1) {
                     if (col_ok) {
@@ -464,7 +564,7 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
                         *reinterpret_cast<float2*>(oV) = make_float2(v0, v1);
                         *reinterpret_cast<float2*>(oD) = make_float2(d0, d1);
                     }
-                    oA += p.nc; oH += p.nc; oV += p.nc; oD += p.nc;
+                    oA += nc_o; oH += nc_o; oV += nc_o; oD += nc_o;
                 }
                 q++;
             }
@@ -481,6 +581,8 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
         }
     }
     TL(6, threadIdx.x == 0);
+    // this strip of the chunk is complete: release it to the next level's items
+    if (p.items && L.keep_a) signal_blocks(p.ctrl + L.flag_off + plane * L.nb, L.fr_shift, y0, ny);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -502,97 +604,406 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-template <int HLEN>
-static int launch_fwd_stream(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
-                             cudaStream_t s)
+// ---- plans of the cross-level launches (host side) ---------------------------------------------------------------------
+// One plan = the ordered item queue of one (direction, geometry, batch) on one stream, plus its control block on the
+// device (ticket counter + completion counters).  Plans live in the filter handle that the transform was called with
+// (one per Wavelets object), so two objects never share counters.
+struct StreamPlan {
+    int dir, dev, hlen, Nr, Nc, batch, nlev, nslots;
+    cudaStream_t stream;
+    int4* d_items = nullptr;
+    unsigned* d_ctrl = nullptr;
+    unsigned nitems = 0, epoch = 0;
+    int flag_off[kMaxLv], fr_shift[kMaxLv], nb[kMaxLv];
+    size_t nctrl = 0;
+    bool dirty = false;      // a launch failed: the counters are out of step with `epoch`
+};
+struct StreamPlans {
+    std::mutex mu;
+    std::vector<StreamPlan*> v;
+};
+StreamPlans* stream_plans_create() { return new StreamPlans(); }
+void stream_plans_destroy(StreamPlans* ps)
 {
-    using G = FwdGeom<HLEN>;
-    const int nr = Nr / 2, nc = Nc / 2;
-    // shapes the TMA staging can serve (see the file header); 0 = "not handled"
-    if ((Nr & 1) || (Nc & 3) || Nc < G::WW || Nr < HLEN) return 0;
-    if ((((uintptr_t)src.p) & 15) || (src.stride & 3)) return 0;
-    if ((((uintptr_t)A.p | (uintptr_t)H.p | (uintptr_t)V.p | (uintptr_t)D.p) & 7) || (A.stride & 1) || (H.stride & 1))
-        return 0;
-    static PerDeviceOnce once;
-    static int per_sm_dev[64];   // resident CTAs per SM (standard variant), per device
-    const bool first = once.first();
-    int& per_sm = per_sm_dev[once.dev];
-    if (first) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_fwd2d_stream<HLEN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        PDWT_CUDA(cudaFuncSetAttribute(k_fwd2d_stream<HLEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(G::SMEM > kTwoPerSmBytes ? G::SMEM : kTwoPerSmBytes)));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd2d_stream<HLEN, false>, G::THREADS, G::SMEM) != cudaSuccess || per_sm < 1) {
-            cudaGetLastError();
-            per_sm = 3;
+    if (!ps) return;
+    for (StreamPlan* pl : ps->v) {
+        if (pl->d_items) cudaFree(pl->d_items);
+        if (pl->d_ctrl) cudaFree(pl->d_ctrl);
+        delete pl;
+    }
+    delete ps;
+}
+
+// one work item of the queue as the host sees it
+struct QItem {
+    int level, plane, r0, nrows, col;   // what the kernel gets
+    float cost;                         // estimated duration (row-pair units, start-up included)
+    int dep0, dep1;                     // (level > 0) virtual counter-block range of level-1, same plane, it waits for
+    int b0, b1;                         // counter blocks of its own level that it completes
+};
+struct QLevel {
+    int nb, ncol;                       // counter blocks per plane; items that cover one block (column blocks)
+};
+
+// Queue order = the dispatch order of a list-scheduling simulation of the launch: `nslots` resident CTAs, every CTA
+// that retires is replaced by the next item of the queue.  Items that read an approximation produced inside the launch
+// become eligible `margin` after the simulated completion of the counter blocks they wait for and are then dispatched
+// BEFORE further level-1 work (deepest level first): they arrive shortly after their input has been written (it is
+// still in L2), they rarely have to spin, and the latency-bound small levels are spread between the bandwidth-bound
+// large items instead of forming a tail of their own.  Inside a plane the chunk that needs the periodic wrap (row 0
+// reads the producer's LAST rows) goes last, so the other chunks can follow the producer row by row.
+static void schedule_queue(const std::vector<QItem>& items, int nlev, const QLevel* lv, int batch, int nslots, float margin,
+                           std::vector<int4>& out)
+{
+    std::vector<std::vector<int>> byl(nlev);
+    for (int i = 0; i < (int)items.size(); i++) byl[items[i].level].push_back(i);
+    std::vector<size_t> head(nlev, 0);
+    std::vector<std::vector<int>> left(nlev);
+    std::vector<std::vector<float>> done(nlev);
+    for (int l = 0; l < nlev; l++) {
+        left[l].assign((size_t)lv[l].nb * batch, lv[l].ncol);
+        done[l].assign((size_t)lv[l].nb * batch, 0.f);
+    }
+    typedef std::pair<float, int> Ev;
+    std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> running;   // (finish time, item)
+    std::priority_queue<float, std::vector<float>, std::greater<float>> slots;
+    for (int i = 0; i < nslots; i++) slots.push(0.f);
+    out.clear();
+    out.reserve(items.size());
+    auto ready_at = [&](const QItem& it) -> float {   // time from which the item may be dispatched; < 0: not known yet
+        const int l = it.level - 1, nb = lv[l].nb;
+        float t = 0.f;
+        for (int v = it.dep0; v <= it.dep1; v++) {
+            int j = v % nb;
+            if (j < 0) j += nb;
+            const size_t k = (size_t)it.plane * nb + j;
+            if (left[l][k] > 0) return -1.f;
+            t = std::max(t, done[l][k]);
+        }
+        return t + margin;
+    };
+    size_t guard = 0;
+    const size_t guard_max = items.size() * 64 + 1024;
+    while (out.size() < items.size()) {
+        const float t = slots.top();
+        while (!running.empty() && running.top().first <= t) {
+            const QItem& it = items[running.top().second];
+            for (int b = it.b0; b <= it.b1; b++) {
+                const size_t k = (size_t)it.plane * lv[it.level].nb + b;
+                if (--left[it.level][k] == 0) done[it.level][k] = running.top().first;
+            }
+            running.pop();
+        }
+        int pick = -1;
+        for (int l = nlev - 1; l >= 1 && pick < 0; l--) {
+            if (head[l] >= byl[l].size()) continue;
+            const float r = ready_at(items[byl[l][head[l]]]);
+            if (r >= 0.f && r <= t) pick = l;
+        }
+        if (pick < 0 && head[0] < byl[0].size()) pick = 0;
+        if (pick < 0 || ++guard > guard_max) {
+            if (running.empty() || guard > guard_max) {   // cannot happen with consistent inputs: finish in natural order
+                for (int l = 0; l < nlev; l++)
+                    for (; head[l] < byl[l].size(); head[l]++) {
+                        const QItem& it = items[byl[l][head[l]]];
+                        out.push_back(make_int4(it.level | (it.plane << 4), it.r0, it.nrows, it.col));
+                    }
+                break;
+            }
+            // only dependent items are left and none is eligible: this slot idles until the next completion (+ margin)
+            slots.pop();
+            slots.push(std::max(t, running.top().first + margin) + 1e-3f);
+            continue;
+        }
+        const int i = byl[pick][head[pick]++];
+        const QItem& it = items[i];
+        slots.pop();
+        slots.push(t + it.cost);
+        running.push(Ev(t + it.cost, i));
+        out.push_back(make_int4(it.level | (it.plane << 4), it.r0, it.nrows, it.col));
+    }
+}
+
+static float plan_margin()
+{
+    static const float m = []() { const char* e = getenv("PDWT_MARGIN"); return e ? (float)atof(e) : 20.f; }();
+    return m;
+}
+
+// find the plan or build it from `items`
+static int get_plan(StreamPlans* ps, int dir, int hlen, int Nr, int Nc, int batch, int nlev, int nslots,
+                    const std::function<void(std::vector<QItem>&, QLevel*, int*)>& make_items, cudaStream_t s, StreamPlan** out)
+{
+    int dev = 0;
+    PDWT_CUDA(cudaGetDevice(&dev));
+    for (StreamPlan* pl : ps->v) {
+        if (pl->dir == dir && pl->dev == dev && pl->stream == s && pl->hlen == hlen && pl->Nr == Nr && pl->Nc == Nc &&
+            pl->batch == batch && pl->nlev == nlev && pl->nslots == nslots) {
+            *out = pl;
+            return PDWT_OK;
         }
     }
+    if (ps->v.size() >= 16) {   // a handle that keeps changing geometry: drop the oldest plan (its stream may still run
+        StreamPlan* old = ps->v.front();   // it, so wait for that stream first)
+        cudaStreamSynchronize(old->stream);
+        cudaFree(old->d_items);
+        cudaFree(old->d_ctrl);
+        delete old;
+        ps->v.erase(ps->v.begin());
+    }
+    StreamPlan* pl = new StreamPlan();
+    pl->dir = dir; pl->dev = dev; pl->hlen = hlen; pl->Nr = Nr; pl->Nc = Nc; pl->batch = batch; pl->nlev = nlev;
+    pl->nslots = nslots;
+    pl->stream = s;
+    std::vector<QItem> items;
+    QLevel lv[kMaxLv];
+    make_items(items, lv, pl->fr_shift);
+    std::vector<int4> q;
+    schedule_queue(items, nlev, lv, batch, nslots, plan_margin(), q);
+    pl->nitems = (unsigned)q.size();
+    size_t off = 4;   // [0] ticket counter; counters start at a 16-byte boundary
+    for (int k = 0; k < nlev; k++) {
+        pl->flag_off[k] = (int)off;
+        pl->nb[k] = lv[k].nb;
+        off += (size_t)lv[k].nb * batch;
+    }
+    pl->nctrl = off;
+    cudaError_t e = cudaMalloc(&pl->d_items, sizeof(int4) * q.size());
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_ctrl, sizeof(unsigned) * pl->nctrl);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_items, q.data(), sizeof(int4) * q.size(), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pl->d_ctrl, 0, sizeof(unsigned) * pl->nctrl, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // q is pageable and about to go out of scope
+    if (e != cudaSuccess) {
+        if (pl->d_items) cudaFree(pl->d_items);
+        if (pl->d_ctrl) cudaFree(pl->d_ctrl);
+        delete pl;
+        return note_cuda(e);
+    }
+    ps->v.push_back(pl);
+    *out = pl;
+    return PDWT_OK;
+}
+
+// counters out of step after a failed launch: zero them and restart the epochs
+static int plan_prepare(StreamPlan* pl, cudaStream_t s)
+{
+    if (pl->dirty || pl->epoch > 0x3fffffu) {   // (epoch * warps per block must stay far from 2^31)
+        PDWT_CUDA(cudaMemsetAsync(pl->d_ctrl, 0, sizeof(unsigned) * pl->nctrl, s));
+        pl->epoch = 0;
+        pl->dirty = false;
+    }
+    return PDWT_OK;
+}
+
+// largest power of two <= 16 that divides a and b
+static int pow2_div(int a, int b)
+{
+    int f = 16;
+    while (f > 1 && ((a % f) || (b % f))) f >>= 1;
+    return f;
+}
+static int ilog2i(int v)
+{
+    int s = 0;
+    while ((1 << s) < v) s++;
+    return s;
+}
+
+template <int HLEN>
+static bool fwd_stream_eligible(const StreamLevelIO& io)
+{
+    using G = FwdGeom<HLEN>;
+    const int Nr = io.Nr, Nc = io.Nc;
+    // shapes the TMA staging can serve (see the file header)
+    if ((Nr & 1) || (Nc & 3) || Nc < G::WW || Nr < HLEN) return false;
+    if ((((uintptr_t)io.img.p) & 15) || (io.img.stride & 3)) return false;
+    if ((((uintptr_t)io.A.p | (uintptr_t)io.H.p | (uintptr_t)io.V.p | (uintptr_t)io.D.p) & 7) || (io.A.stride & 1) ||
+        (io.H.stride & 1))
+        return false;
+    return true;
+}
+
+// Chunk height of a level launched on its own.  A CTA (NCW strips x TH output rows) costs TH + hlen/2 - 1 row pairs per
+// consumer warp (the vertical halo is row-pass work only, but the accumulators need the same warm-up), an SM holds up to
+// per_sm CTAs and works through the pairs of its resident warps at a roughly constant rate, so the kernel ends when the
+// busiest SM does: minimise (CTAs on the busiest SM) x (pairs per CTA).  For one 4096^2 image that picks TH = 56 (296
+// CTAs = 2 per SM) instead of a power of two that leaves 40 SMs with half the work of the others.
+static int pick_th(int ncg, int nr, int batch, int per_sm, int H2)
+{
+    int TH = 64;
+    const int sms = sm_count();
+    double best = 1e30;
+    for (int th = 128; th >= 4; th -= 2) {
+        const long long ctas = (long long)ncg * idiv_up(nr, th) * batch;
+        const long long full = ctas / ((long long)sms * per_sm), rest = ctas % ((long long)sms * per_sm);
+        const double units = (double)(full * per_sm + (rest + sms - 1) / sms) * (th + H2 - 1);
+        // one CTA per SM = a lone warp per scheduler: measured ~650 cycles per row pair against ~435 per scheduler
+        // with two or more warps sharing it
+        const double cost = units * (ctas <= sms ? 1.5 : 1.0);
+        if (cost < best * 0.999) {
+            best = cost;
+            TH = th;
+        }
+    }
+    return TH;
+}
+
+// Forward levels io[0..nlev): io[l].img (Nr x Nc) -> io[l].A/H/V/D; io[l+1].img must be io[l].A.  Returns the number of
+// LEADING levels it has launched (0 = the first level's shape is not covered), < 0 on error.
+template <int HLEN>
+static int launch_fwd_stream(const Taps& t, StreamPlans* plans, const StreamLevelIO* io, int nlev, int batch, cudaStream_t s)
+{
+    using G = FwdGeom<HLEN>;
+    int n = 0;
+    while (n < nlev && n < kMaxLv && fwd_stream_eligible<HLEN>(io[n])) n++;
+    if (n == 0) return 0;
+    static const bool multi_on = []() { const char* e = getenv("PDWT_MULTI"); return !e || atoi(e) != 0; }();
+    if (!plans || !multi_on) n = 1;
+    static PerDeviceOnce once;
+    static int per_sm_dev[64];   // resident CTAs per SM (standard variant), per device
+    int dev = 0;
+    {
+        const cudaError_t eo = once.run([&]() -> cudaError_t {
+            int d = 0, per_sm = 0;
+            cudaError_t e = cudaGetDevice(&d);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(k_fwd2d_stream<HLEN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(k_fwd2d_stream<HLEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(G::SMEM > kTwoPerSmBytes ? G::SMEM : kTwoPerSmBytes));
+            if (e != cudaSuccess) return e;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd2d_stream<HLEN, false>, G::THREADS, G::SMEM) != cudaSuccess || per_sm < 1) {
+                cudaGetLastError();
+                per_sm = 3;
+            }
+            per_sm_dev[d & 63] = per_sm;
+            return cudaSuccess;
+        }, &dev);
+        if (eo != cudaSuccess) return note_cuda(eo);
+    }
+    const int per_sm = per_sm_dev[dev & 63];
     FwdParams<HLEN> p;
-    memset(&p.tm, 0, sizeof p.tm);
-    p.use_tm = 0;
-    if (EncodeTiledFn enc = encode_tiled_fn()) {
-        const cuuint64_t dims[3] = {(cuuint64_t)Nc, (cuuint64_t)Nr, (cuuint64_t)batch};
-        const cuuint64_t strides[2] = {(cuuint64_t)Nc * 4, (cuuint64_t)src.stride * 4};  // bytes, dims 1 and 2
-        const cuuint32_t box[3] = {(cuuint32_t)G::WW, (cuuint32_t)G::SR, 1};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        if (enc(&p.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)src.p, dims, strides, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-            p.use_tm = (getenv("PDWT_NO_TENSORMAP") == nullptr);
+    memset(&p, 0, sizeof p);
+    EncodeTiledFn enc = encode_tiled_fn();
+    const int env_th = []() { const char* e = getenv("PDWT_TH"); return e ? atoi(e) : 0; }();
+    for (int l = 0; l < n; l++) {
+        FwdLevel& L = p.lev[l];
+        const int Nr = io[l].Nr, Nc = io[l].Nc, nr = Nr / 2, nc = Nc / 2;
+        if (enc) {
+            const cuuint64_t dims[3] = {(cuuint64_t)Nc, (cuuint64_t)Nr, (cuuint64_t)batch};
+            const cuuint64_t strides[2] = {(cuuint64_t)Nc * 4, (cuuint64_t)io[l].img.stride * 4};  // bytes, dims 1 and 2
+            const cuuint32_t box[3] = {(cuuint32_t)G::WW, (cuuint32_t)G::SR, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            if (enc(&L.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)io[l].img.p, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                L.use_tm = (getenv("PDWT_NO_TENSORMAP") == nullptr);
+        }
+        L.src = io[l].img.p; L.A = io[l].A.p; L.Hb = io[l].H.p; L.V = io[l].V.p; L.D = io[l].D.p;
+        L.s_src = io[l].img.stride; L.s_a = io[l].A.stride; L.s_d = io[l].H.stride;
+        L.Nr = Nr; L.Nc = Nc; L.nr = nr; L.nc = nc;
+        L.ncg = idiv_up(nc, G::WO * G::NCW);
+        L.TH = env_th > 0 ? env_th : pick_th(L.ncg, nr, batch, per_sm, G::H2);   // a level launched on its own
+        L.nrc = idiv_up(nr, L.TH);
+        L.nstrips = idiv_up(nc, G::WO);
+        L.keep_a = (l + 1 < n) || io[l].a_reused;
     }
     for (int j = 0; j < HLEN; j++) {
         p.lh[j] = make_float2(t.L[HLEN - 1 - j], t.H[HLEN - 1 - j]);
         p.ly[j] = t.L[HLEN - 1 - j];
         p.hy[j] = t.H[HLEN - 1 - j];
     }
-    p.src = src.p; p.A = A.p; p.Hb = H.p; p.V = V.p; p.D = D.p;
-    p.s_src = src.stride; p.s_a = A.stride; p.s_d = H.stride;
-    p.Nr = Nr; p.Nc = Nc; p.nr = nr; p.nc = nc;
-    p.ncg = idiv_up(nc, G::WO * G::NCW);
-    // Chunk height.  A CTA (NCW strips x TH output rows) costs TH + hlen/2 - 1 row pairs per consumer warp (the vertical
-    // halo is row-pass work only, but the scatter accumulators need the same warm-up), an SM holds up to 4 CTAs and
-    // works through the pairs of its resident warps at a roughly constant rate, so the kernel ends when the busiest SM
-    // does: minimise (CTAs on the busiest SM) x (pairs per CTA).  For one 4096^2 image that picks TH = 56 (296 CTAs = 2
-    // per SM) instead of a power of two that leaves 40 SMs with half the work of the others.
-    int TH = 64;
-    {
-        const int sms = sm_count();
-        double best = 1e30;
-        for (int th = 128; th >= 4; th -= 2) {
-            const long long ctas = (long long)p.ncg * idiv_up(nr, th) * batch;
-            const long long full = ctas / ((long long)sms * per_sm), rest = ctas % ((long long)sms * per_sm);
-            const double units = (double)(full * per_sm + (rest + sms - 1) / sms) * (th + G::H2 - 1);
-            // one CTA per SM = a lone warp per scheduler: measured ~650 cycles per row pair against ~435 per scheduler
-            // with two or more warps sharing it
-            const double cost = units * (ctas <= sms ? 1.5 : 1.0);
-            if (cost < best * 0.999) {
-                best = cost;
-                TH = th;
-            }
-        }
-    }
-    if (const char* e = getenv("PDWT_TH")) TH = atoi(e) > 0 ? atoi(e) : TH;
-    p.TH = TH;
     // a consumer needs > 1 us per super-slot and two more are staged behind it: the producer can afford to sleep
     static const unsigned poll_ns = []() { const char* e = getenv("PDWT_POLL_NS"); return e ? (unsigned)atoi(e) : 200u; }();
     p.poll_ns = poll_ns;
     p.pdl_early = pdl_mode() == 1;
-    p.nrc = idiv_up(nr, TH);
-    const long long nctas = (long long)p.ncg * p.nrc * batch;
-    if (nctas > 0x7fffffff) return 0;
-    PDWT_PROF(prof_tag("k_fwd2d_stream", Nr, Nc), s);
-    // at most 2 CTAs per SM: the high-register variant loses no occupancy (PDWT_LOWOCC=0|1 forces the choice)
-    bool lowocc = nctas <= 2LL * sm_count();
+    // at most 2 CTAs of the first level per SM: the high-register variant loses no occupancy (PDWT_LOWOCC=0|1 forces it)
+    bool lowocc = (long long)p.lev[0].ncg * p.lev[0].nrc * batch <= 2LL * sm_count();
     if (const char* e = getenv("PDWT_LOWOCC")) lowocc = atoi(e) != 0;
     // ... and it asks for so much shared memory that NO SM can take a third CTA: the block scheduler does not spread a
     // grid of 2 x SMs CTAs evenly by itself, and the kernel ends with the busiest SM (PDWT_TWOPERSM=0 switches it off)
     static const bool cap2 = []() { const char* e = getenv("PDWT_TWOPERSM"); return !e || atoi(e) != 0; }();
+    long long nctas = 0;
+    StreamPlan* pl = nullptr;
+    std::unique_lock<std::mutex> plan_lock;
+    if (n > 1) {
+        // Row chunks of the queue.  One image: each level keeps the height its own cost model picks.  A batch: 128 rows
+        // (vertical halo 5 %) while plenty of work is left, tapering over the last two planes so that the launch does
+        // not end with a few long items; a level below the first halves the height (its planes have half the rows).
+        auto chunk_rows = [&](int l, int plane) -> int {
+            if (env_th > 0) return env_th;
+            if (batch == 1) return p.lev[l].TH;
+            const int d = batch - 1 - plane;
+            const int base = d >= 2 ? 128 : (d == 1 ? 64 : 32);
+            return std::max(16, base >> l);
+        };
+        auto make_items = [&](std::vector<QItem>& items, QLevel* lv, int* fr_shift) {
+            for (int l = 0; l < n; l++) {
+                int fr = 16;
+                for (int b = 0; b < batch; b++) fr = std::min(fr, pow2_div(p.lev[l].nr, chunk_rows(l, b)));
+                fr_shift[l] = ilog2i(fr);
+                lv[l].nb = p.lev[l].nr / fr;
+                lv[l].ncol = p.lev[l].ncg;
+            }
+            for (int l = 0; l < n; l++)
+                for (int b = 0; b < batch; b++) {
+                    const int th = chunk_rows(l, b), nr = p.lev[l].nr, nch = idiv_up(nr, th);
+                    for (int k = 0; k < nch; k++) {
+                        const int c = (l > 0) ? (k + 1) % nch : k;   // the chunk that needs the wrap goes last
+                        QItem it;
+                        it.level = l; it.plane = b; it.r0 = c * th; it.nrows = std::min(th, nr - it.r0);
+                        it.cost = (float)(it.nrows + G::H2 - 1 + 8);
+                        it.b0 = it.r0 >> fr_shift[l];
+                        it.b1 = (it.r0 + it.nrows - 1) >> fr_shift[l];
+                        it.dep0 = it.dep1 = 0;
+                        if (l > 0) {
+                            const int v0 = 2 * it.r0 - G::C, v1 = v0 + 2 * (it.nrows + G::H2 - 1) - 1;
+                            it.dep0 = v0 >> fr_shift[l - 1];   // arithmetic shift: floor
+                            it.dep1 = v1 >> fr_shift[l - 1];
+                        }
+                        for (int cg = 0; cg < p.lev[l].ncg; cg++) {
+                            it.col = cg;
+                            items.push_back(it);
+                        }
+                    }
+                }
+        };
+        plan_lock = std::unique_lock<std::mutex>(plans->mu);
+        const int nslots = sm_count() * ((lowocc && cap2) ? 2 : per_sm);
+        int rc = get_plan(plans, 0, HLEN, io[0].Nr, io[0].Nc, batch, n, nslots, make_items, s, &pl);
+        if (rc < 0) return rc;
+        rc = plan_prepare(pl, s);
+        if (rc < 0) return rc;
+        for (int l = 0; l < n; l++) {
+            p.lev[l].flag_off = pl->flag_off[l];
+            p.lev[l].fr_shift = pl->fr_shift[l];
+            p.lev[l].nb = pl->nb[l];
+        }
+        p.items = pl->d_items;
+        p.ctrl = pl->d_ctrl;
+        p.ticket_base = pl->epoch * pl->nitems;
+        p.epoch = ++pl->epoch;
+        nctas = pl->nitems;
+    } else {
+        nctas = (long long)p.lev[0].ncg * p.lev[0].nrc * batch;
+    }
+    if (nctas > 0x7fffffff) return 0;
+    PDWT_PROF(prof_tag(n > 1 ? "k_fwd2d_stream_levels" : "k_fwd2d_stream", io[0].Nr, io[0].Nc), s);
+    cudaError_t e;
     if (lowocc)
-        PDWT_CUDA(launch_pdl(k_fwd2d_stream<HLEN, true>, dim3((unsigned)nctas), G::THREADS,
-                             cap2 && G::SMEM < kTwoPerSmBytes ? kTwoPerSmBytes : G::SMEM, s, p));
+        e = launch_pdl(k_fwd2d_stream<HLEN, true>, dim3((unsigned)nctas), G::THREADS,
+                       cap2 && G::SMEM < kTwoPerSmBytes ? kTwoPerSmBytes : G::SMEM, s, p);
     else
-        PDWT_CUDA(launch_pdl(k_fwd2d_stream<HLEN, false>, dim3((unsigned)nctas), G::THREADS, G::SMEM, s, p));
-    PDWT_LAUNCH_CHECK();
-    return 1;
+        e = launch_pdl(k_fwd2d_stream<HLEN, false>, dim3((unsigned)nctas), G::THREADS, G::SMEM, s, p);
+    if (e == cudaSuccess) {
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        if (pl) pl->dirty = true;
+        return note_cuda(e);
+    }
+    return n;
 }
 
 // ================================================================================================== inverse
@@ -627,16 +1038,27 @@ struct InvGeom {
     static_assert(UNR % 2 == 0 && UNR % NSLOT == 0 && DEPTH < RS, "static ring / tile addressing");
 };
 
-template <int HLEN>
-struct InvParams {
-    float il[2][HLEN / 2], ih[2][HLEN / 2];  // [output parity][j]: IL / IH taps in accumulation order
-    float2 lh[2][HLEN / 2];                  // the same as (IL, IH) pairs for the row synthesis
+struct InvLevel {
     const float *A, *Hb, *V, *D;
     float* dst;
     size_t s_a, s_d, s_dst;                  // plane strides (floats)
     int nr, nc, Mr, Mc;                      // coefficient and output plane sizes (Mr = 2 nr, Mc = 2 nc)
-    int TM;                                  // output row PAIRS per chunk
+    int TM;                                  // output row PAIRS per chunk (single-level launches)
     int ncb, nrc;
+    int flag_off;                            // completion counters of this level: ctrl[flag_off + plane * nb + block]
+    int keep_dst;                            // dst is read back by the next level (of this launch or a later kernel)
+    int fr_shift, nb;                        // counter block = 2^fr_shift rows of dst, nb blocks per plane
+    int pad_;
+};
+
+template <int HLEN>
+struct InvParams {
+    InvLevel lev[kMaxLv];                    // lev[0] is the coarsest level of the launch; lev[k].A == lev[k-1].dst
+    float il[2][HLEN / 2], ih[2][HLEN / 2];  // [output parity][j]: IL / IH taps in accumulation order
+    float2 lh[2][HLEN / 2];                  // the same as (IL, IH) pairs for the row synthesis
+    const int4* items;                       // (level | plane << 4, first coefficient row, rows, column block) by ticket; NULL: one level
+    unsigned* ctrl;
+    unsigned ticket_base, epoch;
     int pdl_early;
 };
 
@@ -654,32 +1076,51 @@ __device__ __forceinline__ void cp_async_wait()
 }
 
 template <int HLEN>
-__global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__ InvParams<HLEN> p)
+__global__ void __launch_bounds__(32, HLEN <= 14 ? 16 : 12) k_inv2d_stream(const __grid_constant__ InvParams<HLEN> p)
 {
     using G = InvGeom<HLEN>;
     constexpr int H2 = G::H2, NSLOT = G::NSLOT, WIN = G::WIN, SHIFT = G::SHIFT, UNR = G::UNR, DEPTH = G::DEPTH;
     extern __shared__ __align__(16) unsigned char smem_inv[];
     const int lane = threadIdx.x;
-    const int item = blockIdx.x;
-    const int cb = item % p.ncb, rest = item / p.ncb, rc = rest % p.nrc, plane = rest / p.nrc;
-    const int k0 = cb * G::WOUT, m0 = rc * p.TM;
-    const int nm = min(p.TM, p.nr - m0);
+    int level = 0, plane, m0, nm, cb;
+    if (p.items) {
+        // lane 0 draws the ticket; the item reaches the warp through warp reductions, whose results live in UNIFORM
+        // registers (CREDUX): everything derived from it stays on the uniform datapath, as with blockIdx
+        int4 it = make_int4(0, 0, 0, 0);
+        if (lane == 0) it = p.items[atomicAdd(p.ctrl, 1u) - p.ticket_base];
+        const int lp = __reduce_max_sync(0xffffffffu, (unsigned)it.x);
+        level = lp & 15;
+        plane = lp >> 4;
+        m0 = __reduce_max_sync(0xffffffffu, (unsigned)it.y);
+        nm = __reduce_max_sync(0xffffffffu, (unsigned)it.z);
+        cb = __reduce_max_sync(0xffffffffu, (unsigned)it.w);
+    } else {
+        const int item = blockIdx.x, ncb0 = p.lev[0].ncb, nrc0 = p.lev[0].nrc;
+        cb = item % ncb0;
+        const int rest = item / ncb0;
+        plane = rest / nrc0;
+        m0 = (rest % nrc0) * p.lev[0].TM;
+        nm = min(p.lev[0].TM, p.lev[0].nr - m0);
+    }
+    const InvLevel& L = p.lev[level];
+    const int nr = L.nr, nc = L.nc, Mc = L.Mc;
+    const int k0 = cb * G::WOUT;
 
     // ---- column synthesis side: this lane owns coefficient columns (col, col+1) of the strip, wrapped periodically
     int col = k0 - G::ALC + 2 * lane;
-    col += (col < 0) ? p.nc : 0;
-    col -= (col >= p.nc) ? p.nc : 0;
+    col += (col < 0) ? nc : 0;
+    col -= (col >= nc) ? nc : 0;
     int lrow = m0 - G::CC;                    // next coefficient row to load (wrapped: separable.cu:265-273)
-    lrow += (lrow < 0) ? p.nr : 0;
-    int to_wrap = p.nr - lrow;
+    lrow += (lrow < 0) ? nr : 0;
+    int to_wrap = nr - lrow;
     // ONE running per-lane pointer (into A) and three uniform byte distances to the same element of H, V, D: per row
     // that is a 64-bit add for each address and one for the advance, nothing else
-    const char* pa = reinterpret_cast<const char*>(p.A + (size_t)plane * p.s_a + (size_t)lrow * p.nc + col);
-    const ptrdiff_t plane_d = (ptrdiff_t)((size_t)plane * p.s_d) - (ptrdiff_t)((size_t)plane * p.s_a);
-    const ptrdiff_t dH = (reinterpret_cast<const char*>(p.Hb) - reinterpret_cast<const char*>(p.A)) + 4 * plane_d;
-    const ptrdiff_t dV = (reinterpret_cast<const char*>(p.V) - reinterpret_cast<const char*>(p.A)) + 4 * plane_d;
-    const ptrdiff_t dD = (reinterpret_cast<const char*>(p.D) - reinterpret_cast<const char*>(p.A)) + 4 * plane_d;
-    const ptrdiff_t row_b = 4 * (ptrdiff_t)p.nc, wrap_b = 4 * (ptrdiff_t)p.nc * p.nr;
+    const char* pa = reinterpret_cast<const char*>(L.A + (size_t)plane * L.s_a + (size_t)lrow * nc + col);
+    const ptrdiff_t plane_d = (ptrdiff_t)((size_t)plane * L.s_d) - (ptrdiff_t)((size_t)plane * L.s_a);
+    const ptrdiff_t dH = (reinterpret_cast<const char*>(L.Hb) - reinterpret_cast<const char*>(L.A)) + 4 * plane_d;
+    const ptrdiff_t dV = (reinterpret_cast<const char*>(L.V) - reinterpret_cast<const char*>(L.A)) + 4 * plane_d;
+    const ptrdiff_t dD = (reinterpret_cast<const char*>(L.D) - reinterpret_cast<const char*>(L.A)) + 4 * plane_d;
+    const ptrdiff_t row_b = 4 * (ptrdiff_t)nc, wrap_b = 4 * (ptrdiff_t)nc * nr;
 
     // Coefficient rows travel global -> shared -> registers.  Each lane prefetches ITS OWN two columns of A, H, V, D
     // DEPTH rows ahead with 8-byte cp.async copies into a private 32-byte cell per ring row, and later reads the same
@@ -700,7 +1141,7 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
             pa += row_b;
             if (--to_wrap == 0) {
                 pa -= wrap_b;
-                to_wrap = p.nr;
+                to_wrap = nr;
             }
         }
         cp_async_commit();
@@ -725,8 +1166,13 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
     for (int i = 0; i < NSLOT; i++) wA[i] = wH[i] = wV[i] = wD[i] = 0ull;
     TL(0, lane == 0);
     if (p.pdl_early) pdl_launch_dependents();
-    pdl_wait();        // the previous level's kernel (or whatever wrote the coefficients) has completed
+    pdl_wait();        // the previous kernel of the stream (whatever wrote the coefficients) has completed
     TL(1, lane == 0);
+    if (level > 0) {
+        // A was written by items of the previous (coarser) level of this launch: wait for the row chunks this chunk reads
+        const InvLevel& P = p.lev[level - 1];
+        wait_blocks(p.ctrl + P.flag_off + plane * P.nb, P.fr_shift, P.nb, p.epoch * (unsigned)P.ncb, m0 - G::CC, nm + WIN - 1);
+    }
 #pragma unroll
     for (int i = 0; i < DEPTH; i++) issue_row(i);
 #pragma unroll
@@ -737,14 +1183,15 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
     const int g = lane >> 4, lq = lane & 15;
     const int px0 = 2 * k0 + 8 * lq;
     const bool row_lane = lq < G::LPR;
-    float* out = p.dst + (size_t)plane * p.s_dst + (size_t)(2 * m0 + g) * p.Mc + px0;
-    const bool st0 = row_lane && px0 + 4 <= p.Mc, st1 = row_lane && px0 + 8 <= p.Mc;
+    float* out = L.dst + (size_t)plane * L.s_dst + (size_t)(2 * m0 + g) * Mc + px0;
+    const bool st0 = row_lane && px0 + 4 <= Mc, st1 = row_lane && px0 + 8 <= Mc;
     // tile addressing (see InvGeom): the writer stores chunk `lane`, the reader loads chunks 2*lq + v
     unsigned char* const tile_wr = smem_inv + 16 * ((lane >> 1) + (lane & 1) * G::ODD0);
     const unsigned char* const tile_rd = smem_inv + g * G::TROWB + 16 * lq;
 
     int s = 0;
-    for (;;) {
+    bool more = true;
+    while (more) {
 #pragma unroll
         for (int u = 0; u < UNR; u++) {       // body: UNR output row pairs; register, ring and tile indices all static
 #ifdef PDWT_EXPERIMENTS
@@ -756,7 +1203,10 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
                 tl_stamp(blockIdx.x, 6);
             }
 #endif
-            if (s >= nm) return;
+            if (s >= nm) {
+                more = false;
+                break;
+            }
             if (s + 1 >= nm) pdl_launch_dependents();
             if (s + 1 < nm) load_row(u + WIN);   // the row that the NEXT pair adds to the window (one pair of slack)
             const int sb = u % NSLOT, buf = u & 1;
@@ -804,22 +1254,80 @@ __global__ void __launch_bounds__(32, 12) k_inv2d_stream(const __grid_constant__
                 if (st0) *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
                 if (st1) *reinterpret_cast<float4*>(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
             }
-            out += 2 * (size_t)p.Mc;
+            out += 2 * (size_t)Mc;
             s++;
         }
     }
+    // this block of the chunk is complete: release it to the next level's items
+    if (p.items && L.keep_dst) signal_blocks(p.ctrl + L.flag_off + plane * L.nb, L.fr_shift, 2 * m0, 2 * nm);
 }
 
 template <int HLEN>
-static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr,
-                             int Mc, int batch, cudaStream_t s)
+static bool inv_stream_eligible(const StreamLevelIO& io)
 {
     using G = InvGeom<HLEN>;
-    if (Mr != 2 * nr || Mc != 2 * nc || (nc & 1) || nc < 64 || nr < G::WIN) return 0;
-    if ((((uintptr_t)A.p | (uintptr_t)H.p | (uintptr_t)V.p | (uintptr_t)D.p) & 7) || (A.stride & 1) || (H.stride & 1))
-        return 0;
-    if ((((uintptr_t)dst.p) & 15) || (dst.stride & 3)) return 0;
+    const int Mr = io.Nr, Mc = io.Nc, nr = Mr / 2, nc = Mc / 2;
+    if ((Mr & 1) || (Mc & 1) || (nc & 1) || nc < 64 || nr < G::WIN) return false;
+    if ((((uintptr_t)io.A.p | (uintptr_t)io.H.p | (uintptr_t)io.V.p | (uintptr_t)io.D.p) & 7) || (io.A.stride & 1) ||
+        (io.H.stride & 1))
+        return false;
+    if ((((uintptr_t)io.img.p) & 15) || (io.img.stride & 3)) return false;
+    return true;
+}
+
+// Chunk height (output row PAIRS per one-warp CTA) of a level launched on its own.  An item costs TM loop iterations plus a
+// prologue worth ~2.5 of them (WIN-1 extra coefficient rows and the pipeline fill); items are spread over sms x per_sm
+// resident warps, so the kernel takes about ceil(items / slots) x (TM + 2.5): pick the TM that minimises it (4096^2:
+// TM = 32, exactly one item per slot).
+static int pick_tm(int ncb, int nr, int batch, int per_sm)
+{
+    int TM = 32;
+    const long long slots = (long long)sm_count() * per_sm;
+    double best = 1e30;
+    for (int tm = 64; tm >= 2; tm--) {
+        const long long items = (long long)ncb * idiv_up(nr, tm) * batch;
+        const double cost = (double)((items + slots - 1) / slots) * (tm + 2.5);
+        if (cost < best * 0.999) {
+            best = cost;
+            TM = tm;
+        }
+    }
+    return TM;
+}
+
+// Inverse levels io[0..nlev), coarsest first: io[l].A/H/V/D (Nr/2 x Nc/2) -> io[l].img (Nr x Nc); io[l+1].A must be
+// io[l].img.  Returns the number of LEADING levels launched (0 = the first level's shape is not covered), < 0 on error.
+template <int HLEN>
+static int launch_inv_stream(const Taps& t, StreamPlans* plans, const StreamLevelIO* io, int nlev, int batch, cudaStream_t s)
+{
+    using G = InvGeom<HLEN>;
+    int n = 0;
+    while (n < nlev && n < kMaxLv && inv_stream_eligible<HLEN>(io[n])) n++;
+    if (n == 0) return 0;
+    static const bool multi_on = []() { const char* e = getenv("PDWT_MULTI"); return !e || atoi(e) != 0; }();
+    if (!plans || !multi_on) n = 1;
+    static PerDeviceOnce once;
+    static int per_sm_dev[64];
+    int dev = 0;
+    {
+        const cudaError_t eo = once.run([&]() -> cudaError_t {
+            int d = 0, per_sm = 0;
+            cudaError_t e = cudaGetDevice(&d);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(k_inv2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+            if (e != cudaSuccess) return e;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv2d_stream<HLEN>, 32, G::SMEM) != cudaSuccess || per_sm < 1) {
+                cudaGetLastError();
+                per_sm = 12;
+            }
+            per_sm_dev[d & 63] = per_sm;
+            return cudaSuccess;
+        }, &dev);
+        if (eo != cudaSuccess) return note_cuda(eo);
+    }
+    const int per_sm = per_sm_dev[dev & 63];
     InvParams<HLEN> p;
+    memset(&p, 0, sizeof p);
     for (int par = 0; par < 2; par++) {
         const int off = par ? G::SHIFT : 1 - G::SHIFT;
         for (int j = 0; j < HLEN / 2; j++) {
@@ -828,48 +1336,91 @@ static int launch_inv_stream(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2
             p.lh[par][j] = make_float2(p.il[par][j], p.ih[par][j]);
         }
     }
-    p.A = A.p; p.Hb = H.p; p.V = V.p; p.D = D.p; p.dst = dst.p;
-    p.s_a = A.stride; p.s_d = H.stride; p.s_dst = dst.stride;
-    p.nr = nr; p.nc = nc; p.Mr = Mr; p.Mc = Mc;
-    p.ncb = idiv_up(nc, G::WOUT);
-    // Chunk height (output row PAIRS per one-warp CTA).  An item costs TM loop iterations plus a prologue worth ~2.5 of
-    // them (WIN-1 extra coefficient rows and the pipeline fill); items are spread over sms x per_sm resident warps, so
-    // the kernel takes about ceil(items / slots) x (TM + 2.5): pick the TM that minimises it (4096^2: TM = 32, exactly
-    // one item per slot).
-    static PerDeviceOnce once;
-    static int per_sm_dev[64];
-    const bool first = once.first();
-    int& per_sm = per_sm_dev[once.dev];
-    if (first) {
-        PDWT_CUDA(cudaFuncSetAttribute(k_inv2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv2d_stream<HLEN>, 32, G::SMEM) != cudaSuccess || per_sm < 1) {
-            cudaGetLastError();
-            per_sm = 12;
-        }
+    const int env_tm = []() { const char* e = getenv("PDWT_TM"); return e ? atoi(e) : 0; }();
+    for (int l = 0; l < n; l++) {
+        InvLevel& L = p.lev[l];
+        const int Mr = io[l].Nr, Mc = io[l].Nc, nr = Mr / 2, nc = Mc / 2;
+        L.A = io[l].A.p; L.Hb = io[l].H.p; L.V = io[l].V.p; L.D = io[l].D.p; L.dst = io[l].img.p;
+        L.s_a = io[l].A.stride; L.s_d = io[l].H.stride; L.s_dst = io[l].img.stride;
+        L.nr = nr; L.nc = nc; L.Mr = Mr; L.Mc = Mc;
+        L.ncb = idiv_up(nc, G::WOUT);
+        L.TM = env_tm > 0 ? env_tm : pick_tm(L.ncb, nr, batch, per_sm);   // a level launched on its own
+        L.nrc = idiv_up(nr, L.TM);
+        L.keep_dst = (l + 1 < n) || io[l].a_reused;
     }
-    int TM = 32;
-    {
-        const long long slots = (long long)sm_count() * per_sm;
-        double best = 1e30;
-        for (int tm = 64; tm >= 2; tm--) {
-            const long long items = (long long)p.ncb * idiv_up(nr, tm) * batch;
-            const double cost = (double)((items + slots - 1) / slots) * (tm + 2.5);
-            if (cost < best * 0.999) {
-                best = cost;
-                TM = tm;
-            }
-        }
-    }
-    if (const char* e = getenv("PDWT_TM")) TM = atoi(e) > 0 ? atoi(e) : TM;
-    p.TM = TM;
-    p.nrc = idiv_up(nr, TM);
     p.pdl_early = pdl_mode() == 1;
-    const long long nitems = (long long)p.ncb * p.nrc * batch;
+    long long nitems = 0;
+    StreamPlan* pl = nullptr;
+    std::unique_lock<std::mutex> plan_lock;
+    if (n > 1) {
+        // Row chunks (output row PAIRS) of the queue: one image keeps each level's own cost model; a batch uses 32 pairs
+        // and halves them on the last plane, whose finest level is what the launch ends with.
+        auto chunk_rows = [&](int l, int plane) -> int {
+            if (env_tm > 0) return env_tm;
+            if (batch == 1) return p.lev[l].TM;
+            return (batch - 1 - plane >= 1) ? 32 : 16;
+        };
+        auto make_items = [&](std::vector<QItem>& items, QLevel* lv, int* fr_shift) {
+            for (int l = 0; l < n; l++) {
+                int fr = 16;
+                for (int b = 0; b < batch; b++) fr = std::min(fr, pow2_div(p.lev[l].Mr, 2 * chunk_rows(l, b)));
+                fr_shift[l] = ilog2i(fr);
+                lv[l].nb = p.lev[l].Mr / fr;
+                lv[l].ncol = p.lev[l].ncb;
+            }
+            for (int l = 0; l < n; l++)
+                for (int b = 0; b < batch; b++) {
+                    const int tm = chunk_rows(l, b), nr = p.lev[l].nr, nch = idiv_up(nr, tm);
+                    for (int k = 0; k < nch; k++) {
+                        const int c = (l > 0) ? (k + 1) % nch : k;   // the chunk that needs the wrap goes last
+                        QItem it;
+                        it.level = l; it.plane = b; it.r0 = c * tm; it.nrows = std::min(tm, nr - it.r0);
+                        it.cost = (float)(it.nrows + G::WIN + 3);
+                        it.b0 = (2 * it.r0) >> fr_shift[l];
+                        it.b1 = (2 * (it.r0 + it.nrows) - 1) >> fr_shift[l];
+                        it.dep0 = it.dep1 = 0;
+                        if (l > 0) {
+                            const int v0 = it.r0 - G::CC, v1 = v0 + it.nrows + G::WIN - 1 - 1;
+                            it.dep0 = v0 >> fr_shift[l - 1];   // arithmetic shift: floor
+                            it.dep1 = v1 >> fr_shift[l - 1];
+                        }
+                        for (int cb = 0; cb < p.lev[l].ncb; cb++) {
+                            it.col = cb;
+                            items.push_back(it);
+                        }
+                    }
+                }
+        };
+        plan_lock = std::unique_lock<std::mutex>(plans->mu);
+        int rc = get_plan(plans, 1, HLEN, io[n - 1].Nr, io[n - 1].Nc, batch, n, sm_count() * per_sm, make_items, s, &pl);
+        if (rc < 0) return rc;
+        rc = plan_prepare(pl, s);
+        if (rc < 0) return rc;
+        for (int l = 0; l < n; l++) {
+            p.lev[l].flag_off = pl->flag_off[l];
+            p.lev[l].fr_shift = pl->fr_shift[l];
+            p.lev[l].nb = pl->nb[l];
+        }
+        p.items = pl->d_items;
+        p.ctrl = pl->d_ctrl;
+        p.ticket_base = pl->epoch * pl->nitems;
+        p.epoch = ++pl->epoch;
+        nitems = pl->nitems;
+    } else {
+        nitems = (long long)p.lev[0].ncb * p.lev[0].nrc * batch;
+    }
     if (nitems > 0x7fffffff) return 0;
-    PDWT_PROF(prof_tag("k_inv2d_stream", Mr, Mc), s);
-    PDWT_CUDA(launch_pdl(k_inv2d_stream<HLEN>, dim3((unsigned)nitems), 32, G::SMEM, s, p));
-    PDWT_LAUNCH_CHECK();
-    return 1;
+    PDWT_PROF(prof_tag(n > 1 ? "k_inv2d_stream_levels" : "k_inv2d_stream", io[n - 1].Nr, io[n - 1].Nc), s);
+    cudaError_t e = launch_pdl(k_inv2d_stream<HLEN>, dim3((unsigned)nitems), 32, G::SMEM, s, p);
+    if (e == cudaSuccess) {
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        if (pl) pl->dirty = true;
+        return note_cuda(e);
+    }
+    return n;
 }
 
 #ifdef PDWT_EXPERIMENTS
@@ -896,16 +1447,14 @@ namespace pdwt {
         default: return 0;                          \
     }
 
-int s_dwt2_fwd_level(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
-                     cudaStream_t s)
+int s_dwt2_fwd_levels(const Taps& t, StreamPlans* plans, const StreamLevelIO* lv, int nlev, int batch, cudaStream_t s)
 {
-    PDWT_STREAM_HLEN_SWITCH(launch_fwd_stream, t, src, A, H, V, D, Nr, Nc, batch, s)
+    PDWT_STREAM_HLEN_SWITCH(launch_fwd_stream, t, plans, lv, nlev, batch, s)
 }
 
-int s_dwt2_inv_level(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int nr, int nc, int Mr, int Mc,
-                     int batch, cudaStream_t s)
+int s_dwt2_inv_levels(const Taps& t, StreamPlans* plans, const StreamLevelIO* lv, int nlev, int batch, cudaStream_t s)
 {
-    PDWT_STREAM_HLEN_SWITCH(launch_inv_stream, t, A, H, V, D, dst, nr, nc, Mr, Mc, batch, s)
+    PDWT_STREAM_HLEN_SWITCH(launch_inv_stream, t, plans, lv, nlev, batch, s)
 }
 
 }  // namespace pdwt

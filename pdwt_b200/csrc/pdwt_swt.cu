@@ -405,11 +405,8 @@ static int launch_swt_fwd(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 
     PDWT_PROF(prof_tag("k_swt_fwd_fused", Nr, f), s);
 #define PDWT_SWT_FWD(FF)                                                                                                 \
     do {                                                                                                                 \
-        static PerDeviceOnce once;                                                                                       \
-        if (once.first()) {                                                                                              \
-            PDWT_CUDA(cudaFuncSetAttribute(k_swt_fwd_fused<HLEN, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                           (int)kSwtSmemCap));                                                           \
-        }                                                                                                                \
+        PDWT_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_swt_fwd_fused<HLEN, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                  (int)kSwtSmemCap));                                                    \
         PDWT_CUDA(launch_pdl(k_swt_fwd_fused<HLEN, FF>, grid, kSwtThreads, smem, s, t, (const float*)src.p, src.stride,  \
                              A.p, A.stride, H.p, V.p, D.p, H.stride, Nr, Nc, f));                                        \
     } while (0)
@@ -442,11 +439,8 @@ static int launch_swt_inv(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D,
     ht.one = make_float2(1.0f, 1.0f);
 #define PDWT_SWT_INV(FF)                                                                                                 \
     do {                                                                                                                 \
-        static PerDeviceOnce once;                                                                                       \
-        if (once.first()) {                                                                                              \
-            PDWT_CUDA(cudaFuncSetAttribute(k_swt_inv_fused<HLEN, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                           (int)kSwtSmemCap));                                                           \
-        }                                                                                                                \
+        PDWT_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_swt_inv_fused<HLEN, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                  (int)kSwtSmemCap));                                                    \
         PDWT_CUDA(launch_pdl(k_swt_inv_fused<HLEN, FF>, grid, kSwtThreads, smem, s, ht, (const float*)A.p, A.stride,     \
                              (const float*)H.p, (const float*)V.p, (const float*)D.p, H.stride, dst.p, dst.stride, Nr,   \
                              Nc, f));                                                                                    \

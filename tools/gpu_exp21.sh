@@ -1,0 +1,14 @@
+#!/bin/bash
+# r02 exp21: cross-level launches (tickets + row-chunk counters), L2 hints
+O=gpurun_out/exp21; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log; tail -5 $O/pytest.log
+run() { timeout 120 env "$@" python tools/time_step.py $SHAPE 2>&1 | tail -1 | tee -a $O/times.txt; }
+for SHAPE in "4096 4096 1" "4096 4096 8" "2048 2048 64"; do
+  run PDWT_MULTI=0 PDWT_L2_HINTS=0
+  run PDWT_MULTI=0
+  run PDWT_L2_HINTS=0
+  run PDWT_LAG=2
+  run PDWT_LAG=1
+  run PDWT_LAG=3
+  run PDWT_LOWOCC=1
+done

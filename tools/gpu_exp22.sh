@@ -1,0 +1,16 @@
+#!/bin/bash
+O=gpurun_out/exp22; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log; tail -5 $O/pytest.log
+if grep -q failed $O/pytest.log; then
+  timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "stream and sym8-512x1280" > $O/sanitizer.log 2>&1; grep -m 20 -A12 "Invalid\|ERROR SUMMARY\|error" $O/sanitizer.log | head -80
+fi
+run() { timeout 120 env "$@" python tools/time_step.py $SHAPE 2>&1 | tail -1 | tee -a $O/times.txt; }
+for SHAPE in "4096 4096 1" "4096 4096 8" "2048 2048 64"; do
+  run PDWT_MULTI=0 PDWT_L2_HINTS=0
+  run PDWT_MULTI=0
+  run PDWT_L2_HINTS=0
+  run PDWT_LAG=2
+  run PDWT_LAG=1
+  run PDWT_LAG=3
+  run PDWT_LOWOCC=1
+done
