@@ -88,8 +88,8 @@ const char* pdwt_wavelet_name(int i);
  *              reference's allocation size (level-1 size for the DWT, full size for the SWT, common.cu:402-422).
  *   d_tmp    : device scratch, batch * 2*Nr*Nc floats (wt.cu:128-130).
  *   stream   : a cudaStream_t (NULL = legacy default stream, the reference's behaviour).
- * Forward leaves A_L in d_coeffs[0] (no D2D fix-up copies); inverse overwrites d_image, d_coeffs[0] and d_tmp
- * like the reference (wt.cu:273-307).  Results: see DESIGN.md "Arithmetic contract".
+* Forward leaves A_L in d_coeffs[0] (no D2D fix-up copies); inverse overwrites d_image and d_tmp like the reference
+ * (wt.cu:273-307) and MAY overwrite d_coeffs[0] (the generic two-pass kernels do, the fused families keep it).  Results: see DESIGN.md "Arithmetic contract".
  * --------------------------------------------------------------------------------------------------------- */
 #define PDWT_DRIVER_ARGS const pdwt_filters *f, float *d_image, float **d_coeffs, float *d_tmp, pdwt_w_info winfos, \
                          int batch, void *stream
@@ -188,6 +188,9 @@ int pdwt_wavelets_set_stream(pdwt_wavelets* w, void* stream);
  * stream (use pinned host memory and pdwt_wavelets_sync before touching it); several objects on different streams
  * then overlap H2D, kernels and D2H.  Default 0 = the reference's blocking copies (wt.cu:421-434). */
 int pdwt_wavelets_set_async(pdwt_wavelets* w, int on);
+/* norm1 / norm2sq right after a threshold return sums the threshold kernel produced on its way; call this after
+ * writing coefficients through pdwt_wavelets_coeff_int_ptr() behind the object's back */
+int pdwt_wavelets_invalidate_norm_cache(pdwt_wavelets* w);
 
 /* public data members of the class, wt.h:24-33 */
 int pdwt_wavelets_state(const pdwt_wavelets* w);

@@ -10,8 +10,13 @@
  * Differences in behaviour are listed in DESIGN.md ("Deliberate deviations"); the ones visible here: filters are
  * per instance (no process-global constant memory), an unknown wavelet name yields state == W_CREATION_ERROR
  * instead of hanging, norm2sq() returns the sum of squares also for 1-D transforms, CUDA errors are recorded in
- * `last_error` instead of being ignored, and the methods of SURVEY section 2.1 rows 11-13 that are outside the
- * hot path (group_soft_threshold, shrink, proj_linf, circshift, add_wavelet) are not provided.
+ * `last_error` instead of being ignored, and inverse() leaves d_coeffs[0] intact on the fused kernel families.
+ * get_image() / get_coeff() return the element count like the reference, saturated at INT_MAX for batches of 2^31
+ * floats or more (0 still means failure).
+ *
+ * norm1() / norm2sq() right after soft_threshold() / hard_threshold() return sums that the threshold kernel produced
+ * on its way (no second pass over the coefficients).  Writes through the raw pointers of coeff_int_ptr() are invisible
+ * to that cache: call invalidate_norm_cache() after modifying coefficients behind the object's back.
  */
 #ifndef WT_H
 #define WT_H
@@ -84,6 +89,7 @@ class Wavelets {
     int norm1_batched(DTYPE* out);
     int norm2sq_batched(DTYPE* out);
     long long launch_count() const { return launches; }
+    void invalidate_norm_cache() { norm_cache = 0; }   // after writes through coeff_int_ptr()
 
   private:
     Wavelets& operator=(const Wavelets&);  // "do not use" in the reference (wt.cu:36-73)

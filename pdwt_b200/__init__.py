@@ -119,6 +119,7 @@ def lib() -> C.CDLL:
     L.pdwt_wavelets_set_filters_inverse.argtypes = [vp, _fp, _fp]
     L.pdwt_wavelets_set_stream.argtypes = [vp, vp]
     L.pdwt_wavelets_set_async.argtypes = [vp, ci]
+    L.pdwt_wavelets_invalidate_norm_cache.argtypes = [vp]
     L.pdwt_wavelets_info.argtypes = [vp]
     L.pdwt_wavelets_info.restype = WInfo
     L.pdwt_wavelets_wname.argtypes = [vp]
@@ -271,7 +272,15 @@ class Wavelets:
         return self._L.pdwt_wavelets_image_int_ptr(self._h)
 
     def coeff_int_ptr(self, num: int) -> int:
+        """raw device pointer of sub-band `num` (wt.cu:665).  norm1()/norm2sq() right after a threshold return sums the
+        threshold kernel produced on its way: after WRITING through this pointer call invalidate_norm_cache()."""
         return self._L.pdwt_wavelets_coeff_int_ptr(self._h, num)
+
+    def invalidate_norm_cache(self):
+        _check(self._L.pdwt_wavelets_invalidate_norm_cache(self._h), "invalidate_norm_cache")
+
+    def _cuda_error(self) -> str:
+        return f"CUDA error {self._L.pdwt_last_cuda_error()}: {self._L.pdwt_last_cuda_error_string().decode()}"
 
     def set_stream(self, stream):
         """cudaStream_t (int) or torch.cuda.Stream all subsequent work is enqueued on"""
@@ -355,8 +364,8 @@ class Wavelets:
         if out is None:
             out = np.empty(self._plane_shape(w.Nr, w.Nc), dtype=np.float32)
         n = self._L.pdwt_wavelets_get_image(self._h, out.ctypes.data_as(C.c_void_p))
-        if n != out.size:
-            raise PdwtError("get_image failed")
+        if n != min(out.size, 0x7fffffff):   # the reference's int element count, saturated for huge batches
+            raise PdwtError(f"get_image failed ({self._cuda_error()})")
         return out
 
     def coeff_shape(self, num: int):
@@ -369,8 +378,8 @@ class Wavelets:
             return None  # wt.cu:476-479
         out = np.empty(self._plane_shape(*self.coeff_shape(num)), dtype=np.float32)
         n = self._L.pdwt_wavelets_get_coeff(self._h, out.ctypes.data_as(C.c_void_p), num)
-        if n != out.size:
-            raise PdwtError("get_coeff failed")
+        if n != min(out.size, 0x7fffffff):
+            raise PdwtError(f"get_coeff failed ({self._cuda_error()})")
         return out
 
     def set_image(self, img):

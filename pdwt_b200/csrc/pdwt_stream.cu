@@ -205,58 +205,126 @@ struct FwdGeom {
 
 // ---- cross-level execution (one launch per direction for all levels of a transform) --------------------------------
 // The reference queues one pair of kernels per level, each waiting for the previous one's last thread block
-// (separable.cu:179-209, 332-364), and every intermediate approximation makes a round trip through DRAM.  Here the work
-// items of ALL levels (and all planes of a batch) form ONE ordered queue served by one launch: a CTA draws a ticket,
-// looks its item up, and -- if the item reads an approximation produced inside the launch -- waits until the row chunks
-// it needs are complete (one counter per producing row chunk, bumped with a gpu-scope release by every finishing warp).
-// Items are ordered so that producers sit well ahead of their consumers in the queue (image-major, the small levels of
-// plane b interleaved with level 1 of plane b+lag), so the wait is normally over before it starts, the approximation is
-// still in the 126 MB L2 when it is read, and the latency-bound small levels overlap the bandwidth-bound level 1.
-// Tickets (not blockIdx) make this deadlock-free: every item with a smaller ticket is already running or done.
-// Counters are cumulative over launches (`epoch`), so nothing has to be zeroed between launches.
+// (separable.cu:179-209, 332-364).  Here the work items of ALL levels (and all planes of a batch) are served by ONE
+// launch with a small dataflow runtime on the device:
+//   * an item = one CTA's work: (level, plane, row chunk, column block).  Level-1 items (forward: the finest level;
+//     inverse: the coarsest) need nothing from the launch; they are handed out by a ticket counter in natural order.
+//   * every other item reads an approximation produced inside the launch.  Each producing level keeps one completion
+//     counter per block of 2^fr_shift output rows and plane; every warp that finishes a chunk bumps the counters of the
+//     blocks it covers (acq_rel), the LAST arrival at a block bumps the counter of every dependent chunk (all column
+//     blocks of one row chunk of the next level), and the arrival that completes a chunk pushes its items into the
+//     ready queue.
+//   * a CTA that starts takes a READY dependent item if there is one (its input was written microseconds ago and is
+//     still in the 126 MB L2; the latency-bound small levels spread between the bandwidth-bound large items instead of
+//     forming a tail of launches), else the next level-1 ticket, else it claims the next queue position and waits for it.
+// Nothing ever waits while holding resources that its producers need: an item is only started when its input is
+// complete (or when nothing else is left), so the scheme cannot deadlock whatever order the hardware starts CTAs in.
+// Counters are cumulative over launches (`epoch`), queue entries carry the epoch, the two ticket counters alternate by
+// launch parity (a launch's first ticket zeroes the other one): nothing has to be reset between launches.
 constexpr int kMaxLv = 6;
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
 {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_inc(unsigned* p)
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v)
 {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// Completion counters: one per block of 2^fr_shift output rows of a producing level and plane (nb blocks per plane; the
-// level's row count is a multiple of the block).  Every warp that finishes a chunk bumps the counters of the blocks it
-// covers; a block is complete for launch `epoch` at epoch * (warps per block).
-// wait (the whole warp, converged) until every block that intersects the periodic row range [r0, r0 + nrows) is
-// complete.  Each lane polls another block and the loop condition is a vote: a spin loop run by ONE lane makes ptxas
-// treat the rest of the kernel as possibly diverged (BSSY/BSYNC around every branch, WARPSYNC, the uniform datapath lost:
-// the level-1 inverse kernel went from 33 to 50 us).
-__device__ __forceinline__ void wait_blocks(const unsigned* flags, int fr_shift, int nb, unsigned target, int r0, int nrows)
+__device__ __forceinline__ unsigned atom_inc_acqrel(unsigned* p)
 {
-    const int lane = threadIdx.x & 31;
-    const int vb0 = r0 >> fr_shift, vb1 = (r0 + nrows - 1) >> fr_shift;   // arithmetic shift = floor for rows < 0
+    unsigned o;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(o) : "l"(p) : "memory");
+    return o;
+}
+
+struct QCtl {
+    const int4* items;          // (level | plane << 4, first row, rows, column block); NULL: one level, item = blockIdx
+    const int4* chunks;         // per dependent chunk: (blocks it waits for, first item, items, 0)
+    const int* dep_off;         // per (producing level, plane, block): its range in dep_list
+    const int* dep_list;        // dependent chunks
+    unsigned* ctrl;             // [0],[1] ticket counters (launch parity), [2] queue head, [3] queue tail, counters behind
+    unsigned long long* queue;  // ready items: epoch << 32 | item
+    unsigned n0, basehp, epoch; // level-1 items; queue positions used by earlier launches; number of this launch (1, 2, ..)
+    int cc_off;                 // chunk counters: ctrl[cc_off + chunk]
+};
+struct QLevelCtl {
+    int flag_off;               // block counters of this level: ctrl[flag_off + plane * nb + block]
+    int dep_base;               // dep_off index of (this level, plane 0, block 0)
+    int fr_shift, nb;           // block = 2^fr_shift output rows, nb blocks per plane
+    int arrivals;               // warps that bump a block's counter per launch
+    int signals;                // this level's output is read by items of the launch
+};
+
+// The item this CTA works on.  Called by one CONVERGED warp; the result is warp-uniform (it comes out of a warp reduction,
+// i.e. a uniform register).  Lane 0 does the atomics, but every loop condition is a vote: a data-dependent loop run by a
+// single lane makes ptxas treat the rest of the kernel as possibly diverged (BSSY/BSYNC around every branch, WARPSYNC,
+// the uniform datapath lost -- the level-1 inverse kernel went from 33 to 50 us that way).
+__device__ __forceinline__ int q_wait_entry(const QCtl& q, unsigned pos)
+{
+    unsigned long long v;
     for (;;) {
-        bool ok = true;
-        for (int base = vb0; base <= vb1; base += 32) {
-            const int i = base + lane;
-            int j = i % nb;
-            j += (j < 0) ? nb : 0;
-            if (i <= vb1) ok = ok && (int)(ld_acquire_u32(flags + j) - target) >= 0;
-        }
-        if (__all_sync(0xffffffffu, ok)) break;
-        __nanosleep(100);
+        v = ld_acquire_u64(q.queue + pos);   // every lane polls the same word
+        if (__all_sync(0xffffffffu, (unsigned)(v >> 32) == q.epoch)) break;
+        __nanosleep(200);
     }
+    return (int)__reduce_max_sync(0xffffffffu, (unsigned)v);
 }
-// this warp's share of output rows [y0, y0 + ny) is complete and stored: release it
-__device__ __forceinline__ void signal_blocks(unsigned* flags, int fr_shift, int y0, int ny)
+__device__ __forceinline__ int q_take(const QCtl& q)
+{
+    const bool lane0 = (threadIdx.x & 31) == 0;
+    unsigned* c = q.ctrl;
+    volatile unsigned* vc = c;
+    {   // a dependent item that is ready goes before further level-1 work.  The position is claimed with a plain
+        // atomicAdd (a CAS loop collapses under contention: thousands of one-warp CTAs start at once); CTAs racing for the
+        // last ready items may claim positions that are filled a little later and wait for them.
+        unsigned h = 0, t = 0;
+        if (lane0) {
+            h = vc[2];
+            t = vc[3];
+        }
+        if (__any_sync(0xffffffffu, (int)(t - h) > 0)) {
+            unsigned pos = 0;
+            if (lane0) pos = atomicAdd(c + 2, 1u) - q.basehp;
+            return q_wait_entry(q, __reduce_max_sync(0xffffffffu, pos));
+        }
+    }
+    unsigned* t0 = c + (q.epoch & 1);
+    unsigned tk = 0xffffffffu;
+    if (lane0 && *(volatile unsigned*)t0 < q.n0) {
+        tk = atomicAdd(t0, 1u);
+        if (tk == 0) atomicExch(c + ((q.epoch & 1) ^ 1), 0u);   // for the next launch
+    }
+    tk = __reduce_min_sync(0xffffffffu, tk);
+    if (tk < q.n0) return (int)tk;
+    unsigned pos = 0;   // only dependent items are left: claim the next queue position and wait for it
+    if (lane0) pos = atomicAdd(c + 2, 1u) - q.basehp;
+    return q_wait_entry(q, __reduce_max_sync(0xffffffffu, pos));
+}
+// one warp: its share of output rows [r0, r0 + nrows) of (level, plane) is stored
+__device__ __forceinline__ void q_signal(const QCtl& q, const QLevelCtl& L, int plane, int r0, int nrows)
 {
     const int lane = threadIdx.x & 31;
     __syncwarp();
-    const int b0 = y0 >> fr_shift, b1 = (y0 + ny - 1) >> fr_shift;
-    for (int base = b0; base <= b1; base += 32)
-        if (base + lane <= b1) red_release_inc(flags + base + lane);
+    const int b0 = r0 >> L.fr_shift, b1 = (r0 + nrows - 1) >> L.fr_shift;
+    unsigned* blk = q.ctrl + L.flag_off + plane * L.nb;
+    const int* doff = q.dep_off + L.dep_base + plane * L.nb;
+    for (int base = b0; base <= b1; base += 32) {
+        const int i = base + lane;
+        if (i > b1) continue;
+        if (atom_inc_acqrel(blk + i) + 1 != q.epoch * (unsigned)L.arrivals) continue;
+        // last arrival at this block: tell the chunks that wait for it
+        for (int d = doff[i]; d < doff[i + 1]; d++) {
+            const int c = q.dep_list[d];
+            const int4 ch = q.chunks[c];
+            if (atom_inc_acqrel(q.ctrl + q.cc_off + c) + 1 != q.epoch * (unsigned)ch.x) continue;
+            const unsigned pos = atomicAdd(q.ctrl + 3, (unsigned)ch.z) - q.basehp;   // the chunk is complete: its items are ready
+            for (int k = 0; k < ch.z; k++)
+                st_release_u64(q.queue + pos + k, ((unsigned long long)q.epoch << 32) | (unsigned)(ch.y + k));
+        }
+    }
 }
 
 struct alignas(64) FwdLevel {
@@ -268,10 +336,7 @@ struct alignas(64) FwdLevel {
     int TH;                  // output rows per chunk (single-level launches; queue items carry their own rows)
     int ncg, nrc;            // column groups (NCW strips each), row chunks
     int use_tm;
-    int nstrips;             // consumer warps per row = increments of a block's counter per launch
-    int flag_off;            // counters of this level: ctrl[flag_off + plane * nb + block]
-    int keep_a;              // A is read back by the next level of this launch: its items wait on these counters
-    int fr_shift, nb;        // counter block = 2^fr_shift output rows, nb blocks per plane
+    QLevelCtl q;             // completion counters of this level (cross-level launches)
 };
 
 template <int HLEN>
@@ -280,10 +345,7 @@ struct FwdParams {
     float2 lh[HLEN];  // (L[hlen-1-j], H[hlen-1-j]): row-pass tap pairs in the reference's accumulation order
     float ly[HLEN];   // L[hlen-1-j]
     float hy[HLEN];   // H[hlen-1-j]
-    const int4* items;       // (level | plane << 4, first output row, rows, column group) by ticket; NULL: one level, item = blockIdx
-    unsigned* ctrl;          // [0] ticket counter, row-chunk counters behind it (cumulative over launches)
-    unsigned ticket_base;    // tickets handed out by earlier launches
-    unsigned epoch;          // number of this launch (1, 2, ...): a chunk of level l is complete at epoch * nstrips(l)
+    QCtl q;                  // the launch's work queue (q.items == NULL: one level, item = blockIdx)
     int pdl_early;           // PDWT_PDL=1: let the next kernel's CTAs in as soon as this one has started
     unsigned poll_ns;        // producer: sleep between two rounds of polling that found no free ring slot
 };
@@ -335,12 +397,15 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NCW * NSS * 2; i++) mbar_init(bar_s + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (p.items) s_item = p.items[atomicAdd(p.ctrl, 1u) - p.ticket_base];
+    }
+    if (p.q.items && warp == 0) {   // one converged warp draws the item
+        const int idx = q_take(p.q);
+        if (lane == 0) s_item = p.q.items[idx];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();   // the only block-wide barrier: after it the warps only meet through mbarriers
     int level = 0, plane, y0, ny, cg;
-    if (p.items) {     // through warp reductions: their results live in uniform registers (CREDUX), see the inverse kernel
+    if (p.q.items) {   // through warp reductions: their results live in uniform registers (CREDUX), see the inverse kernel
         const int4 it = s_item;
         const int lp = __reduce_max_sync(0xffffffffu, (unsigned)it.x);
         level = lp & 15;
@@ -375,13 +440,9 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
         const float* src = L.src + (size_t)plane * L.s_src;
         const CUtensorMap* tm = &L.tm;
         const bool use_tm = L.use_tm != 0;
-        if (level > 0) {
-            // the source is the approximation written by level-1 items of this launch: wait for the row chunks this
-            // chunk reads (rows past its last pair inside the last super-slot are staged but never used)
-            const FwdLevel& P = p.lev[level - 1];
-            wait_blocks(p.ctrl + P.flag_off + plane * P.nb, P.fr_shift, P.nb, p.epoch * (unsigned)P.nstrips, vr0, 2 * npairs);
-            asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes -> the TMA engine's reads
-        }
+        // level > 0: the source was written by other CTAs of this launch (generic proxy); the item was only handed out
+        // once those rows were complete (acquire in q_take, then the block barrier): order the TMA engine's reads behind it
+        if (level > 0) asm volatile("fence.proxy.async.global;" ::: "memory");
         TL(2, lane == 0);   // dependencies satisfied
         // super-slot k of strip w -> ring slot k % NSS
         auto issue = [&](const int k, const int w) {
@@ -489,7 +550,9 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
     float* oV = L.V + (size_t)plane * L.s_d + o0;
     float* oD = L.D + (size_t)plane * L.s_d + o0;
     // this lane's window inside a staged row, as a generic pointer (plain loads keep their order w.r.t. the barriers)
-    const char* lane_ring = static_cast<const char*>(__cvta_shared_to_generic(my_ring)) + 2 * NC * lane * 4;
+    unsigned lane_off = 2 * NC * lane * 4;
+    asm volatile("" : "+r"(lane_off));   // opaque: otherwise ptxas re-derives it from SR_TID (S2R, ~25 cycles) in front of every row pair
+    const char* lane_ring = static_cast<const char*>(__cvta_shared_to_generic(my_ring)) + lane_off;
 
     // row pass, w_kern_forward_pass1 (separable.cu:91-131): (lo, hi)[c] = sum_j x[2k - C + j] * (L, H)[hlen-1-j]
     auto row_pass = [&](const float (&xv)[G::NV * 4], u64 (&lohi)[NC]) {
@@ -513,62 +576,66 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
         }
     };
 
+    // The output pointers run H2-1 rows AHEAD of the stores (a row leaves when its last tap has arrived, H2-1 pairs after
+    // its first): they advance every pair and the stores are predicated, so a row pair is straight-line code -- with a
+    // branch around the stores ptxas has to agree on ONE register assignment at every merge point and shifts the
+    // accumulator file with 14 MOVs per pair.
+    oA -= (size_t)(H2 - 1) * nc_o; oH -= (size_t)(H2 - 1) * nc_o; oV -= (size_t)(H2 - 1) * nc_o; oD -= (size_t)(H2 - 1) * nc_o;
     int q = 0;                                    // row pair index within the chunk
+    // one row pair whose two rows sit at `rowp` / `rowp + WW floats` of the ring
+    auto pair_step = [&](const char* rowp) {
+        float xa[G::NV * 4], xb[G::NV * 4];
+        load_row(xa, rowp);
+        load_row(xb, rowp + G::WW * 4);
+        if (q + 1 >= npairs) pdl_launch_dependents();   // last row pair of this warp
+        u64 lohi0[NC], lohi1[NC];
+        row_pass(xa, lohi0);
+        // column pass, w_kern_forward_pass2 (separable.cu:135-176), scatter form: the first row of the pair is tap
+        // j = 2*pp of the output row pp pairs back (in place) ...
+#pragma unroll
+        for (int pp = 0; pp < H2; pp++) {
+            const u64 kl = pack2(p.ly[2 * pp], p.ly[2 * pp]), kh = pack2(p.hy[2 * pp], p.hy[2 * pp]);
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                aLV[pp][c] = ffma2(lohi0[c], kl, pp == 0 ? 0ull : aLV[pp][c]);
+                aHD[pp][c] = ffma2(lohi0[c], kh, pp == 0 ? 0ull : aHD[pp][c]);
+            }
+        }
+        row_pass(xb, lohi1);
+        // ... the second row is tap j = 2*pp + 1, and its result moves one slot up: next pair it is pp+1 back
+#pragma unroll
+        for (int pp = H2 - 1; pp >= 0; pp--) {
+            const u64 kl = pack2(p.ly[2 * pp + 1], p.ly[2 * pp + 1]), kh = pack2(p.hy[2 * pp + 1], p.hy[2 * pp + 1]);
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                aLV[pp + 1][c] = ffma2(lohi1[c], kl, aLV[pp][c]);
+                aHD[pp + 1][c] = ffma2(lohi1[c], kh, aHD[pp][c]);
+            }
+        }
+        TL(4, q == 0 && threadIdx.x == 0);
+        // slot H2 received its last tap (j = hlen-1) in this pair
+        if (col_ok && q >= H2 - 1) {
+            float a0, v0, a1, v1, h0, d0, h1, d1;
+            unpack2(aLV[H2][0], a0, v0);
+            unpack2(aLV[H2][1], a1, v1);
+            unpack2(aHD[H2][0], h0, d0);
+            unpack2(aHD[H2][1], h1, d1);
+            *reinterpret_cast<float2*>(oA) = make_float2(a0, a1);
+            *reinterpret_cast<float2*>(oH) = make_float2(h0, h1);
+            *reinterpret_cast<float2*>(oV) = make_float2(v0, v1);
+            *reinterpret_cast<float2*>(oD) = make_float2(d0, d1);
+        }
+        oA += nc_o; oH += nc_o; oV += nc_o; oD += nc_o;
+        q++;
+    };
     unsigned soff = 0, bar = my_bar, parity = 0;  // ring position (byte offset, full barrier, phase) of the super-slot
-    for (int k = 0; k < nss; k++) {
+    const int nfull = npairs / (SR / 2), rem = npairs - nfull * (SR / 2);
+    for (int k = 0; k < nfull; k++) {             // whole super-slots: SR/2 row pairs of straight-line code
         mbar_wait(bar, parity);
         TL(3, threadIdx.x == 0 && k == 0);
         const char* ssp = lane_ring + soff;
 #pragma unroll
-        for (int pin = 0; pin < SR / 2; pin++) {
-            if (q < npairs) {                     // warp-uniform; false only in the tail of the chunk's last super-slot
-                float xa[G::NV * 4], xb[G::NV * 4];
-                load_row(xa, ssp + pin * (2 * G::WW * 4));
-                load_row(xb, ssp + pin * (2 * G::WW * 4) + G::WW * 4);
-                if (q + 1 >= npairs) pdl_launch_dependents();   // last row pair of this warp
-                u64 lohi0[NC], lohi1[NC];
-                row_pass(xa, lohi0);
-                // column pass, w_kern_forward_pass2 (separable.cu:135-176), scatter form: the first row of the pair is
-                // tap j = 2*pp of the output row pp pairs back (in place) ...
-#pragma unroll
-                for (int pp = 0; pp < H2; pp++) {
-                    const u64 kl = pack2(p.ly[2 * pp], p.ly[2 * pp]), kh = pack2(p.hy[2 * pp], p.hy[2 * pp]);
-#pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        aLV[pp][c] = ffma2(lohi0[c], kl, pp == 0 ? 0ull : aLV[pp][c]);
-                        aHD[pp][c] = ffma2(lohi0[c], kh, pp == 0 ? 0ull : aHD[pp][c]);
-                    }
-                }
-                row_pass(xb, lohi1);
-                // ... the second row is tap j = 2*pp + 1, and its result moves one slot up: next pair it is pp+1 back
-#pragma unroll
-                for (int pp = H2 - 1; pp >= 0; pp--) {
-                    const u64 kl = pack2(p.ly[2 * pp + 1], p.ly[2 * pp + 1]), kh = pack2(p.hy[2 * pp + 1], p.hy[2 * pp + 1]);
-#pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        aLV[pp + 1][c] = ffma2(lohi1[c], kl, aLV[pp][c]);
-                        aHD[pp + 1][c] = ffma2(lohi1[c], kh, aHD[pp][c]);
-                    }
-                }
-                TL(4, q == 0 && threadIdx.x == 0);
-                // slot H2 received its last tap (j = hlen-1) in this pair
-                if (q >= H2 - 1) {
-                    if (col_ok) {
-                        float a0, v0, a1, v1, h0, d0, h1, d1;
-                        unpack2(aLV[H2][0], a0, v0);
-                        unpack2(aLV[H2][1], a1, v1);
-                        unpack2(aHD[H2][0], h0, d0);
-                        unpack2(aHD[H2][1], h1, d1);
-                        *reinterpret_cast<float2*>(oA) = make_float2(a0, a1);
-                        *reinterpret_cast<float2*>(oH) = make_float2(h0, h1);
-                        *reinterpret_cast<float2*>(oV) = make_float2(v0, v1);
-                        *reinterpret_cast<float2*>(oD) = make_float2(d0, d1);
-                    }
-                    oA += nc_o; oH += nc_o; oV += nc_o; oD += nc_o;
-                }
-                q++;
-            }
-        }
+        for (int pin = 0; pin < SR / 2; pin++) pair_step(ssp + pin * (2 * G::WW * 4));
         // every lane has consumed all rows of this super-slot: hand it back to the producer
         __syncwarp();
         if (lane == 0) mbar_arrive(bar + 8);
@@ -580,9 +647,15 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
             parity ^= 1;
         }
     }
+    if (rem > 0) {                                // the chunk's last, partial super-slot
+        mbar_wait(bar, parity);
+        TL(3, threadIdx.x == 0 && nfull == 0);
+        const char* ssp = lane_ring + soff;
+        for (int pin = 0; pin < rem; pin++) pair_step(ssp + pin * (2 * G::WW * 4));
+    }
     TL(6, threadIdx.x == 0);
     // this strip of the chunk is complete: release it to the next level's items
-    if (p.items && L.keep_a) signal_blocks(p.ctrl + L.flag_off + plane * L.nb, L.fr_shift, y0, ny);
+    if (p.q.items && L.q.signals) q_signal(p.q, L.q, plane, y0, ny);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -605,18 +678,28 @@ static EncodeTiledFn encode_tiled_fn()
 }
 
 // ---- plans of the cross-level launches (host side) ---------------------------------------------------------------------
-// One plan = the ordered item queue of one (direction, geometry, batch) on one stream, plus its control block on the
-// device (ticket counter + completion counters).  Plans live in the filter handle that the transform was called with
-// (one per Wavelets object), so two objects never share counters.
+// One plan = the item, chunk and dependency tables of one (direction, geometry, batch) on one stream, plus its control
+// block and ready queue on the device.  Plans live in the filter handle that the transform was called with (one per
+// Wavelets object), so two objects never share counters.
 struct StreamPlan {
-    int dir, dev, hlen, Nr, Nc, batch, nlev, nslots;
+    int dir, dev, hlen, Nr, Nc, batch, nlev, variant;
     cudaStream_t stream;
-    int4* d_items = nullptr;
+    int4* d_items = nullptr;   // items, then chunks
+    int* d_dep = nullptr;      // dep_off, then dep_list
     unsigned* d_ctrl = nullptr;
-    unsigned nitems = 0, epoch = 0;
-    int flag_off[kMaxLv], fr_shift[kMaxLv], nb[kMaxLv];
+    unsigned long long* d_queue = nullptr;
+    unsigned nitems = 0, n0 = 0, nhp = 0, nchunks = 0, ndep_off = 0, epoch = 0;
+    QLevelCtl lq[kMaxLv];
+    int cc_off = 0;
     size_t nctrl = 0;
     bool dirty = false;      // a launch failed: the counters are out of step with `epoch`
+    void release()
+    {
+        if (d_items) cudaFree(d_items);
+        if (d_dep) cudaFree(d_dep);
+        if (d_ctrl) cudaFree(d_ctrl);
+        if (d_queue) cudaFree(d_queue);
+    }
 };
 struct StreamPlans {
     std::mutex mu;
@@ -627,118 +710,31 @@ void stream_plans_destroy(StreamPlans* ps)
 {
     if (!ps) return;
     for (StreamPlan* pl : ps->v) {
-        if (pl->d_items) cudaFree(pl->d_items);
-        if (pl->d_ctrl) cudaFree(pl->d_ctrl);
+        pl->release();
         delete pl;
     }
     delete ps;
 }
 
-// one work item of the queue as the host sees it
+// one work item as the host sees it; items are generated level by level, plane by plane, row chunk by row chunk, column
+// block fastest -- the items of one chunk are consecutive
 struct QItem {
     int level, plane, r0, nrows, col;   // what the kernel gets
-    float cost;                         // estimated duration (row-pair units, start-up included)
-    int dep0, dep1;                     // (level > 0) virtual counter-block range of level-1, same plane, it waits for
-    int b0, b1;                         // counter blocks of its own level that it completes
+    int dep0, dep1;                     // (level > 0) virtual block range of level-1, same plane, that it reads (may wrap)
 };
 struct QLevel {
-    int nb, ncol;                       // counter blocks per plane; items that cover one block (column blocks)
+    int nb, arrivals;                   // counter blocks per plane; warps that complete one block
 };
 
-// Queue order = the dispatch order of a list-scheduling simulation of the launch: `nslots` resident CTAs, every CTA
-// that retires is replaced by the next item of the queue.  Items that read an approximation produced inside the launch
-// become eligible `margin` after the simulated completion of the counter blocks they wait for and are then dispatched
-// BEFORE further level-1 work (deepest level first): they arrive shortly after their input has been written (it is
-// still in L2), they rarely have to spin, and the latency-bound small levels are spread between the bandwidth-bound
-// large items instead of forming a tail of their own.  Inside a plane the chunk that needs the periodic wrap (row 0
-// reads the producer's LAST rows) goes last, so the other chunks can follow the producer row by row.
-static void schedule_queue(const std::vector<QItem>& items, int nlev, const QLevel* lv, int batch, int nslots, float margin,
-                           std::vector<int4>& out)
-{
-    std::vector<std::vector<int>> byl(nlev);
-    for (int i = 0; i < (int)items.size(); i++) byl[items[i].level].push_back(i);
-    std::vector<size_t> head(nlev, 0);
-    std::vector<std::vector<int>> left(nlev);
-    std::vector<std::vector<float>> done(nlev);
-    for (int l = 0; l < nlev; l++) {
-        left[l].assign((size_t)lv[l].nb * batch, lv[l].ncol);
-        done[l].assign((size_t)lv[l].nb * batch, 0.f);
-    }
-    typedef std::pair<float, int> Ev;
-    std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> running;   // (finish time, item)
-    std::priority_queue<float, std::vector<float>, std::greater<float>> slots;
-    for (int i = 0; i < nslots; i++) slots.push(0.f);
-    out.clear();
-    out.reserve(items.size());
-    auto ready_at = [&](const QItem& it) -> float {   // time from which the item may be dispatched; < 0: not known yet
-        const int l = it.level - 1, nb = lv[l].nb;
-        float t = 0.f;
-        for (int v = it.dep0; v <= it.dep1; v++) {
-            int j = v % nb;
-            if (j < 0) j += nb;
-            const size_t k = (size_t)it.plane * nb + j;
-            if (left[l][k] > 0) return -1.f;
-            t = std::max(t, done[l][k]);
-        }
-        return t + margin;
-    };
-    size_t guard = 0;
-    const size_t guard_max = items.size() * 64 + 1024;
-    while (out.size() < items.size()) {
-        const float t = slots.top();
-        while (!running.empty() && running.top().first <= t) {
-            const QItem& it = items[running.top().second];
-            for (int b = it.b0; b <= it.b1; b++) {
-                const size_t k = (size_t)it.plane * lv[it.level].nb + b;
-                if (--left[it.level][k] == 0) done[it.level][k] = running.top().first;
-            }
-            running.pop();
-        }
-        int pick = -1;
-        for (int l = nlev - 1; l >= 1 && pick < 0; l--) {
-            if (head[l] >= byl[l].size()) continue;
-            const float r = ready_at(items[byl[l][head[l]]]);
-            if (r >= 0.f && r <= t) pick = l;
-        }
-        if (pick < 0 && head[0] < byl[0].size()) pick = 0;
-        if (pick < 0 || ++guard > guard_max) {
-            if (running.empty() || guard > guard_max) {   // cannot happen with consistent inputs: finish in natural order
-                for (int l = 0; l < nlev; l++)
-                    for (; head[l] < byl[l].size(); head[l]++) {
-                        const QItem& it = items[byl[l][head[l]]];
-                        out.push_back(make_int4(it.level | (it.plane << 4), it.r0, it.nrows, it.col));
-                    }
-                break;
-            }
-            // only dependent items are left and none is eligible: this slot idles until the next completion (+ margin)
-            slots.pop();
-            slots.push(std::max(t, running.top().first + margin) + 1e-3f);
-            continue;
-        }
-        const int i = byl[pick][head[pick]++];
-        const QItem& it = items[i];
-        slots.pop();
-        slots.push(t + it.cost);
-        running.push(Ev(t + it.cost, i));
-        out.push_back(make_int4(it.level | (it.plane << 4), it.r0, it.nrows, it.col));
-    }
-}
-
-static float plan_margin()
-{
-    static const float m = []() { const char* e = getenv("PDWT_MARGIN"); return e ? (float)atof(e) : 20.f; }();
-    return m;
-}
-
-// find the plan or build it from `items`
-static int get_plan(StreamPlans* ps, int dir, int hlen, int Nr, int Nc, int batch, int nlev, int nslots,
+// find the plan or build it: make_items fills the items (level 0 first) and, per level, the block geometry
+static int get_plan(StreamPlans* ps, int dir, int hlen, int Nr, int Nc, int batch, int nlev, int variant,
                     const std::function<void(std::vector<QItem>&, QLevel*, int*)>& make_items, cudaStream_t s, StreamPlan** out)
 {
     int dev = 0;
     PDWT_CUDA(cudaGetDevice(&dev));
     for (StreamPlan* pl : ps->v) {
         if (pl->dir == dir && pl->dev == dev && pl->stream == s && pl->hlen == hlen && pl->Nr == Nr && pl->Nc == Nc &&
-            pl->batch == batch && pl->nlev == nlev && pl->nslots == nslots) {
+            pl->batch == batch && pl->nlev == nlev && pl->variant == variant) {
             *out = pl;
             return PDWT_OK;
         }
@@ -746,36 +742,90 @@ static int get_plan(StreamPlans* ps, int dir, int hlen, int Nr, int Nc, int batc
     if (ps->v.size() >= 16) {   // a handle that keeps changing geometry: drop the oldest plan (its stream may still run
         StreamPlan* old = ps->v.front();   // it, so wait for that stream first)
         cudaStreamSynchronize(old->stream);
-        cudaFree(old->d_items);
-        cudaFree(old->d_ctrl);
+        old->release();
         delete old;
         ps->v.erase(ps->v.begin());
     }
     StreamPlan* pl = new StreamPlan();
     pl->dir = dir; pl->dev = dev; pl->hlen = hlen; pl->Nr = Nr; pl->Nc = Nc; pl->batch = batch; pl->nlev = nlev;
-    pl->nslots = nslots;
+    pl->variant = variant;
     pl->stream = s;
     std::vector<QItem> items;
     QLevel lv[kMaxLv];
-    make_items(items, lv, pl->fr_shift);
-    std::vector<int4> q;
-    schedule_queue(items, nlev, lv, batch, nslots, plan_margin(), q);
-    pl->nitems = (unsigned)q.size();
-    size_t off = 4;   // [0] ticket counter; counters start at a 16-byte boundary
-    for (int k = 0; k < nlev; k++) {
-        pl->flag_off[k] = (int)off;
-        pl->nb[k] = lv[k].nb;
-        off += (size_t)lv[k].nb * batch;
+    int fr_shift[kMaxLv];
+    make_items(items, lv, fr_shift);
+    // control block: [0..3] tickets / queue head / tail, block counters of the producing levels, chunk counters
+    size_t off = 4;
+    int dep_base = 0;
+    for (int l = 0; l < nlev; l++) {
+        QLevelCtl& q = pl->lq[l];
+        q.fr_shift = fr_shift[l];
+        q.nb = lv[l].nb;
+        q.arrivals = lv[l].arrivals;
+        q.signals = l + 1 < nlev;
+        q.flag_off = (int)off;
+        q.dep_base = dep_base;
+        if (q.signals) {
+            off += (size_t)lv[l].nb * batch;
+            dep_base += lv[l].nb * batch;
+        }
     }
+    pl->cc_off = (int)off;
+    // chunks of the dependent levels and the blocks they wait for
+    std::vector<int4> tab(items.size());
+    std::vector<int4> chunks;
+    std::vector<std::vector<int>> deps((size_t)dep_base);
+    unsigned n0 = 0;
+    for (size_t i = 0; i < items.size(); i++) {
+        const QItem& it = items[i];
+        tab[i] = make_int4(it.level | (it.plane << 4), it.r0, it.nrows, it.col);
+        if (it.level == 0) {
+            n0++;
+            continue;
+        }
+        const bool same = !chunks.empty() && i > 0 && items[i - 1].level == it.level && items[i - 1].plane == it.plane &&
+                          items[i - 1].r0 == it.r0;
+        if (same) {
+            chunks.back().z++;
+            continue;
+        }
+        const int c = (int)chunks.size(), lp = it.level - 1, nb = lv[lp].nb;
+        int need = 0;
+        for (int v = it.dep0; v <= it.dep1 && v < it.dep0 + nb; v++) {   // at most every block of the plane once
+            int j = v % nb;
+            if (j < 0) j += nb;
+            deps[(size_t)pl->lq[lp].dep_base + (size_t)it.plane * nb + j].push_back(c);
+            need++;
+        }
+        chunks.push_back(make_int4(need, (int)i, 1, 0));
+    }
+    pl->n0 = n0;
+    pl->nitems = (unsigned)items.size();
+    pl->nhp = pl->nitems - n0;
+    pl->nchunks = (unsigned)chunks.size();
+    off += chunks.size();
     pl->nctrl = off;
-    cudaError_t e = cudaMalloc(&pl->d_items, sizeof(int4) * q.size());
+    std::vector<int> dep_tab(deps.size() + 1);
+    size_t ndl = 0;
+    for (size_t i = 0; i < deps.size(); i++) {
+        dep_tab[i] = (int)ndl;
+        ndl += deps[i].size();
+    }
+    dep_tab[deps.size()] = (int)ndl;
+    pl->ndep_off = (unsigned)dep_tab.size();
+    for (auto& d : deps) dep_tab.insert(dep_tab.end(), d.begin(), d.end());
+    tab.insert(tab.end(), chunks.begin(), chunks.end());
+    cudaError_t e = cudaMalloc(&pl->d_items, sizeof(int4) * tab.size());
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_dep, sizeof(int) * dep_tab.size());
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_ctrl, sizeof(unsigned) * pl->nctrl);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_items, q.data(), sizeof(int4) * q.size(), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_queue, sizeof(unsigned long long) * (pl->nhp + 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_items, tab.data(), sizeof(int4) * tab.size(), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_dep, dep_tab.data(), sizeof(int) * dep_tab.size(), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(pl->d_ctrl, 0, sizeof(unsigned) * pl->nctrl, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // q is pageable and about to go out of scope
+    if (e == cudaSuccess) e = cudaMemsetAsync(pl->d_queue, 0, sizeof(unsigned long long) * (pl->nhp + 1), s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // the host tables are pageable and about to go out of scope
     if (e != cudaSuccess) {
-        if (pl->d_items) cudaFree(pl->d_items);
-        if (pl->d_ctrl) cudaFree(pl->d_ctrl);
+        pl->release();
         delete pl;
         return note_cuda(e);
     }
@@ -784,15 +834,38 @@ static int get_plan(StreamPlans* ps, int dir, int hlen, int Nr, int Nc, int batc
     return PDWT_OK;
 }
 
+// fill the queue part of a launch's parameters and advance the plan by one launch
+static void plan_bind(StreamPlan* pl, QCtl& q)
+{
+    q.items = pl->d_items;
+    q.chunks = pl->d_items + pl->nitems;
+    q.dep_off = pl->d_dep;
+    q.dep_list = pl->d_dep + pl->ndep_off;
+    q.ctrl = pl->d_ctrl;
+    q.queue = pl->d_queue;
+    q.n0 = pl->n0;
+    q.basehp = pl->epoch * pl->nhp;
+    q.epoch = ++pl->epoch;
+    q.cc_off = pl->cc_off;
+}
+
 // counters out of step after a failed launch: zero them and restart the epochs
 static int plan_prepare(StreamPlan* pl, cudaStream_t s)
 {
     if (pl->dirty || pl->epoch > 0x3fffffu) {   // (epoch * warps per block must stay far from 2^31)
         PDWT_CUDA(cudaMemsetAsync(pl->d_ctrl, 0, sizeof(unsigned) * pl->nctrl, s));
+        PDWT_CUDA(cudaMemsetAsync(pl->d_queue, 0, sizeof(unsigned long long) * (pl->nhp + 1), s));
         pl->epoch = 0;
         pl->dirty = false;
     }
     return PDWT_OK;
+}
+
+// PDWT_MULTI=1 (read per call: the tests switch it inside one process) serves all levels of a transform with one launch
+static bool multi_level_on()
+{
+    const char* e = getenv("PDWT_MULTI");
+    return e && atoi(e) != 0;
 }
 
 // largest power of two <= 16 that divides a and b
@@ -857,8 +930,9 @@ static int launch_fwd_stream(const Taps& t, StreamPlans* plans, const StreamLeve
     int n = 0;
     while (n < nlev && n < kMaxLv && fwd_stream_eligible<HLEN>(io[n])) n++;
     if (n == 0) return 0;
-    static const bool multi_on = []() { const char* e = getenv("PDWT_MULTI"); return !e || atoi(e) != 0; }();
-    if (!plans || !multi_on) n = 1;
+    // One launch per level is the default: the cross-level launch (PDWT_MULTI=1) is bit-identical but measured slower on
+    // B200: the level kernels are co-limited by FP32 issue and HBM, so overlapping levels frees nothing.
+    if (!plans || !multi_level_on()) n = 1;
     static PerDeviceOnce once;
     static int per_sm_dev[64];   // resident CTAs per SM (standard variant), per device
     int dev = 0;
@@ -881,7 +955,12 @@ static int launch_fwd_stream(const Taps& t, StreamPlans* plans, const StreamLeve
         }, &dev);
         if (eo != cudaSuccess) return note_cuda(eo);
     }
-    const int per_sm = per_sm_dev[dev & 63];
+    // Two CTAs (8 consumer warps) per SM with the high-register variant is the default for every grid: measured on B200 it
+    // is as fast as or faster than four CTAs of the 96-register variant (8 x 4096^2 level 1: 189 vs 205 us; one image:
+    // 33.1 vs 35.3 us) -- fewer, faster warps and fewer concurrent DRAM streams.  PDWT_LOWOCC=0 selects the other one.
+    bool lowocc = true;
+    if (const char* e = getenv("PDWT_LOWOCC")) lowocc = atoi(e) != 0;
+    const int per_sm = lowocc ? 2 : per_sm_dev[dev & 63];
     FwdParams<HLEN> p;
     memset(&p, 0, sizeof p);
     EncodeTiledFn enc = encode_tiled_fn();
@@ -905,8 +984,6 @@ static int launch_fwd_stream(const Taps& t, StreamPlans* plans, const StreamLeve
         L.ncg = idiv_up(nc, G::WO * G::NCW);
         L.TH = env_th > 0 ? env_th : pick_th(L.ncg, nr, batch, per_sm, G::H2);   // a level launched on its own
         L.nrc = idiv_up(nr, L.TH);
-        L.nstrips = idiv_up(nc, G::WO);
-        L.keep_a = (l + 1 < n) || io[l].a_reused;
     }
     for (int j = 0; j < HLEN; j++) {
         p.lh[j] = make_float2(t.L[HLEN - 1 - j], t.H[HLEN - 1 - j]);
@@ -917,9 +994,6 @@ static int launch_fwd_stream(const Taps& t, StreamPlans* plans, const StreamLeve
     static const unsigned poll_ns = []() { const char* e = getenv("PDWT_POLL_NS"); return e ? (unsigned)atoi(e) : 200u; }();
     p.poll_ns = poll_ns;
     p.pdl_early = pdl_mode() == 1;
-    // at most 2 CTAs of the first level per SM: the high-register variant loses no occupancy (PDWT_LOWOCC=0|1 forces it)
-    bool lowocc = (long long)p.lev[0].ncg * p.lev[0].nrc * batch <= 2LL * sm_count();
-    if (const char* e = getenv("PDWT_LOWOCC")) lowocc = atoi(e) != 0;
     // ... and it asks for so much shared memory that NO SM can take a third CTA: the block scheduler does not spread a
     // grid of 2 x SMs CTAs evenly by itself, and the kernel ends with the busiest SM (PDWT_TWOPERSM=0 switches it off)
     static const bool cap2 = []() { const char* e = getenv("PDWT_TWOPERSM"); return !e || atoi(e) != 0; }();
@@ -943,20 +1017,16 @@ static int launch_fwd_stream(const Taps& t, StreamPlans* plans, const StreamLeve
                 for (int b = 0; b < batch; b++) fr = std::min(fr, pow2_div(p.lev[l].nr, chunk_rows(l, b)));
                 fr_shift[l] = ilog2i(fr);
                 lv[l].nb = p.lev[l].nr / fr;
-                lv[l].ncol = p.lev[l].ncg;
+                lv[l].arrivals = idiv_up(p.lev[l].nc, G::WO);   // every strip (consumer warp) of a row
             }
             for (int l = 0; l < n; l++)
                 for (int b = 0; b < batch; b++) {
                     const int th = chunk_rows(l, b), nr = p.lev[l].nr, nch = idiv_up(nr, th);
                     for (int k = 0; k < nch; k++) {
-                        const int c = (l > 0) ? (k + 1) % nch : k;   // the chunk that needs the wrap goes last
                         QItem it;
-                        it.level = l; it.plane = b; it.r0 = c * th; it.nrows = std::min(th, nr - it.r0);
-                        it.cost = (float)(it.nrows + G::H2 - 1 + 8);
-                        it.b0 = it.r0 >> fr_shift[l];
-                        it.b1 = (it.r0 + it.nrows - 1) >> fr_shift[l];
+                        it.level = l; it.plane = b; it.r0 = k * th; it.nrows = std::min(th, nr - it.r0);
                         it.dep0 = it.dep1 = 0;
-                        if (l > 0) {
+                        if (l > 0) {   // input rows 2 y0 - C .. of the level above, virtual (they may wrap)
                             const int v0 = 2 * it.r0 - G::C, v1 = v0 + 2 * (it.nrows + G::H2 - 1) - 1;
                             it.dep0 = v0 >> fr_shift[l - 1];   // arithmetic shift: floor
                             it.dep1 = v1 >> fr_shift[l - 1];
@@ -969,20 +1039,12 @@ static int launch_fwd_stream(const Taps& t, StreamPlans* plans, const StreamLeve
                 }
         };
         plan_lock = std::unique_lock<std::mutex>(plans->mu);
-        const int nslots = sm_count() * ((lowocc && cap2) ? 2 : per_sm);
-        int rc = get_plan(plans, 0, HLEN, io[0].Nr, io[0].Nc, batch, n, nslots, make_items, s, &pl);
+        int rc = get_plan(plans, 0, HLEN, io[0].Nr, io[0].Nc, batch, n, env_th, make_items, s, &pl);
         if (rc < 0) return rc;
         rc = plan_prepare(pl, s);
         if (rc < 0) return rc;
-        for (int l = 0; l < n; l++) {
-            p.lev[l].flag_off = pl->flag_off[l];
-            p.lev[l].fr_shift = pl->fr_shift[l];
-            p.lev[l].nb = pl->nb[l];
-        }
-        p.items = pl->d_items;
-        p.ctrl = pl->d_ctrl;
-        p.ticket_base = pl->epoch * pl->nitems;
-        p.epoch = ++pl->epoch;
+        for (int l = 0; l < n; l++) p.lev[l].q = pl->lq[l];
+        plan_bind(pl, p.q);
         nctas = pl->nitems;
     } else {
         nctas = (long long)p.lev[0].ncg * p.lev[0].nrc * batch;
@@ -1045,10 +1107,7 @@ struct InvLevel {
     int nr, nc, Mr, Mc;                      // coefficient and output plane sizes (Mr = 2 nr, Mc = 2 nc)
     int TM;                                  // output row PAIRS per chunk (single-level launches)
     int ncb, nrc;
-    int flag_off;                            // completion counters of this level: ctrl[flag_off + plane * nb + block]
-    int keep_dst;                            // dst is read back by the next level (of this launch or a later kernel)
-    int fr_shift, nb;                        // counter block = 2^fr_shift rows of dst, nb blocks per plane
-    int pad_;
+    QLevelCtl q;                             // completion counters of this level (cross-level launches): rows of dst
 };
 
 template <int HLEN>
@@ -1056,9 +1115,7 @@ struct InvParams {
     InvLevel lev[kMaxLv];                    // lev[0] is the coarsest level of the launch; lev[k].A == lev[k-1].dst
     float il[2][HLEN / 2], ih[2][HLEN / 2];  // [output parity][j]: IL / IH taps in accumulation order
     float2 lh[2][HLEN / 2];                  // the same as (IL, IH) pairs for the row synthesis
-    const int4* items;                       // (level | plane << 4, first coefficient row, rows, column block) by ticket; NULL: one level
-    unsigned* ctrl;
-    unsigned ticket_base, epoch;
+    QCtl q;                                  // the launch's work queue (q.items == NULL: one level, item = blockIdx)
     int pdl_early;
 };
 
@@ -1083,11 +1140,12 @@ __global__ void __launch_bounds__(32, HLEN <= 14 ? 16 : 12) k_inv2d_stream(const
     extern __shared__ __align__(16) unsigned char smem_inv[];
     const int lane = threadIdx.x;
     int level = 0, plane, m0, nm, cb;
-    if (p.items) {
+    if (p.q.items) {
         // lane 0 draws the ticket; the item reaches the warp through warp reductions, whose results live in UNIFORM
         // registers (CREDUX): everything derived from it stays on the uniform datapath, as with blockIdx
+        const int idx = q_take(p.q);
         int4 it = make_int4(0, 0, 0, 0);
-        if (lane == 0) it = p.items[atomicAdd(p.ctrl, 1u) - p.ticket_base];
+        if (lane == 0) it = p.q.items[idx];
         const int lp = __reduce_max_sync(0xffffffffu, (unsigned)it.x);
         level = lp & 15;
         plane = lp >> 4;
@@ -1168,11 +1226,9 @@ __global__ void __launch_bounds__(32, HLEN <= 14 ? 16 : 12) k_inv2d_stream(const
     if (p.pdl_early) pdl_launch_dependents();
     pdl_wait();        // the previous kernel of the stream (whatever wrote the coefficients) has completed
     TL(1, lane == 0);
-    if (level > 0) {
-        // A was written by items of the previous (coarser) level of this launch: wait for the row chunks this chunk reads
-        const InvLevel& P = p.lev[level - 1];
-        wait_blocks(p.ctrl + P.flag_off + plane * P.nb, P.fr_shift, P.nb, p.epoch * (unsigned)P.ncb, m0 - G::CC, nm + WIN - 1);
-    }
+    // level > 0: A was written by other CTAs of this launch and the item was handed out once those rows were complete
+    // (acquire by lane 0 in q_take); every lane's own L1-allocating loads come after its own fence
+    if (level > 0) __threadfence();
 #pragma unroll
     for (int i = 0; i < DEPTH; i++) issue_row(i);
 #pragma unroll
@@ -1259,7 +1315,7 @@ __global__ void __launch_bounds__(32, HLEN <= 14 ? 16 : 12) k_inv2d_stream(const
         }
     }
     // this block of the chunk is complete: release it to the next level's items
-    if (p.items && L.keep_dst) signal_blocks(p.ctrl + L.flag_off + plane * L.nb, L.fr_shift, 2 * m0, 2 * nm);
+    if (p.q.items && L.q.signals) q_signal(p.q, L.q, plane, 2 * m0, 2 * nm);
 }
 
 template <int HLEN>
@@ -1304,8 +1360,7 @@ static int launch_inv_stream(const Taps& t, StreamPlans* plans, const StreamLeve
     int n = 0;
     while (n < nlev && n < kMaxLv && inv_stream_eligible<HLEN>(io[n])) n++;
     if (n == 0) return 0;
-    static const bool multi_on = []() { const char* e = getenv("PDWT_MULTI"); return !e || atoi(e) != 0; }();
-    if (!plans || !multi_on) n = 1;
+    if (!plans || !multi_level_on()) n = 1;   // see launch_fwd_stream
     static PerDeviceOnce once;
     static int per_sm_dev[64];
     int dev = 0;
@@ -1346,7 +1401,6 @@ static int launch_inv_stream(const Taps& t, StreamPlans* plans, const StreamLeve
         L.ncb = idiv_up(nc, G::WOUT);
         L.TM = env_tm > 0 ? env_tm : pick_tm(L.ncb, nr, batch, per_sm);   // a level launched on its own
         L.nrc = idiv_up(nr, L.TM);
-        L.keep_dst = (l + 1 < n) || io[l].a_reused;
     }
     p.pdl_early = pdl_mode() == 1;
     long long nitems = 0;
@@ -1366,20 +1420,16 @@ static int launch_inv_stream(const Taps& t, StreamPlans* plans, const StreamLeve
                 for (int b = 0; b < batch; b++) fr = std::min(fr, pow2_div(p.lev[l].Mr, 2 * chunk_rows(l, b)));
                 fr_shift[l] = ilog2i(fr);
                 lv[l].nb = p.lev[l].Mr / fr;
-                lv[l].ncol = p.lev[l].ncb;
+                lv[l].arrivals = p.lev[l].ncb;   // every column block (one warp) of a row
             }
             for (int l = 0; l < n; l++)
                 for (int b = 0; b < batch; b++) {
                     const int tm = chunk_rows(l, b), nr = p.lev[l].nr, nch = idiv_up(nr, tm);
                     for (int k = 0; k < nch; k++) {
-                        const int c = (l > 0) ? (k + 1) % nch : k;   // the chunk that needs the wrap goes last
                         QItem it;
-                        it.level = l; it.plane = b; it.r0 = c * tm; it.nrows = std::min(tm, nr - it.r0);
-                        it.cost = (float)(it.nrows + G::WIN + 3);
-                        it.b0 = (2 * it.r0) >> fr_shift[l];
-                        it.b1 = (2 * (it.r0 + it.nrows) - 1) >> fr_shift[l];
+                        it.level = l; it.plane = b; it.r0 = k * tm; it.nrows = std::min(tm, nr - it.r0);
                         it.dep0 = it.dep1 = 0;
-                        if (l > 0) {
+                        if (l > 0) {   // coefficient rows m0 - CC .. = rows of the coarser level's output, virtual
                             const int v0 = it.r0 - G::CC, v1 = v0 + it.nrows + G::WIN - 1 - 1;
                             it.dep0 = v0 >> fr_shift[l - 1];   // arithmetic shift: floor
                             it.dep1 = v1 >> fr_shift[l - 1];
@@ -1392,19 +1442,12 @@ static int launch_inv_stream(const Taps& t, StreamPlans* plans, const StreamLeve
                 }
         };
         plan_lock = std::unique_lock<std::mutex>(plans->mu);
-        int rc = get_plan(plans, 1, HLEN, io[n - 1].Nr, io[n - 1].Nc, batch, n, sm_count() * per_sm, make_items, s, &pl);
+        int rc = get_plan(plans, 1, HLEN, io[n - 1].Nr, io[n - 1].Nc, batch, n, env_tm, make_items, s, &pl);
         if (rc < 0) return rc;
         rc = plan_prepare(pl, s);
         if (rc < 0) return rc;
-        for (int l = 0; l < n; l++) {
-            p.lev[l].flag_off = pl->flag_off[l];
-            p.lev[l].fr_shift = pl->fr_shift[l];
-            p.lev[l].nb = pl->nb[l];
-        }
-        p.items = pl->d_items;
-        p.ctrl = pl->d_ctrl;
-        p.ticket_base = pl->epoch * pl->nitems;
-        p.epoch = ++pl->epoch;
+        for (int l = 0; l < n; l++) p.lev[l].q = pl->lq[l];
+        plan_bind(pl, p.q);
         nitems = pl->nitems;
     } else {
         nitems = (long long)p.lev[0].ncb * p.lev[0].nrc * batch;

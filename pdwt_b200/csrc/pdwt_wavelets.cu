@@ -191,7 +191,16 @@ Wavelets::Wavelets(DTYPE* img, int Nr, int Nc, const char* name, int levels, int
     const size_t a_elems = pdwt_coeff_alloc_elems(winfos, 0) * batch;
     W_TRY(cuda_rc(cudaMalloc(&d_coeffs[0], sizeof(DTYPE) * a_elems)), W_CREATION_ERROR);
     W_TRY(cuda_rc(cudaMemset(d_coeffs[0], 0, sizeof(DTYPE) * a_elems)), W_CREATION_ERROR);
-
+    if (do_cycle_spinning && do_swt)   // wt.cu:173
+        puts("Warning: makes little sense to use Cycle spinning with stationary Wavelet transform");
+    if (do_cycle_spinning && ndim == 1) {   // wt.cu:175-179
+        puts("ERROR: cycle spinning is not implemented for 1D. Use SWT instead.");
+        last_error = PDWT_ERR_ARG;
+        state = W_CREATION_ERROR;
+    }
+    // The fills and copies above ran on the legacy default stream, which does NOT order against the non-blocking
+    // stream the object may be given next (set_stream): they must have landed before the constructor returns.
+    W_TRY(cuda_rc(cudaDeviceSynchronize()), W_CREATION_ERROR);
 }
 
 // Copy constructor (deep), reference wt.cu:191-222
@@ -202,6 +211,9 @@ Wavelets::Wavelets(const Wavelets& W)
 {
     memcpy(wname, W.wname, sizeof wname);
     if (winfos.Nr < 1 || winfos.Nc < 1) return;
+    // the copies below run on the legacy default stream: whatever the source's own (possibly non-blocking) stream still
+    // has in flight must be complete first
+    W_TRY(cuda_rc(cudaStreamSynchronize((cudaStream_t)W.stream)), W_CREATION_ERROR);
     W_TRY(alloc_buffers(), W_CREATION_ERROR);
     const size_t plane = (size_t)winfos.Nr * winfos.Nc;
     W_TRY(cuda_rc(cudaMemcpy(d_image, W.d_image, sizeof(DTYPE) * plane * batch, cudaMemcpyDeviceToDevice)),
@@ -230,6 +242,7 @@ Wavelets::Wavelets(const Wavelets& W)
     W_TRY(cuda_rc(cudaMalloc(&d_coeffs[0], sizeof(DTYPE) * a_elems)), W_CREATION_ERROR);
     W_TRY(cuda_rc(cudaMemcpy(d_coeffs[0], W.d_coeffs[0], sizeof(DTYPE) * a_elems, cudaMemcpyDeviceToDevice)),
           W_CREATION_ERROR);
+    W_TRY(cuda_rc(cudaDeviceSynchronize()), W_CREATION_ERROR);   // as in the image constructor
 }
 
 Wavelets::~Wavelets() { free_buffers(); }
@@ -476,7 +489,7 @@ int Wavelets::get_image(DTYPE* img)
         last_error = rc;
         return 0;
     }
-    return (int)n;
+    return n > 0x7fffffffull ? 0x7fffffff : (int)n;   // the reference's int count, saturated
 }
 
 // reference wt.cu:427-434
@@ -512,7 +525,7 @@ static int copy_coeff(Wavelets* W, DTYPE* host_or_dev, int num, cudaMemcpyKind k
         W->last_error = note_cuda(e);
         return 0;
     }
-    return (int)(n * W->batch);
+    return n * W->batch > 0x7fffffffull ? 0x7fffffff : (int)(n * W->batch);
 }
 
 // reference wt.cu:475-508
@@ -746,7 +759,20 @@ int pdwt_wavelets_sync(pdwt_wavelets* w)
 int pdwt_wavelets_set_stream(pdwt_wavelets* w, void* stream)
 {
     CHECK_W;
-    w->W.stream = stream;
+    if (w->W.stream != stream) {
+        // the norm cache is published in the order of the stream that ran the threshold: finish that stream's work
+        // before the object moves on, and forget the cache
+        const int rc = note_cuda(cudaStreamSynchronize((cudaStream_t)w->W.stream));
+        w->W.invalidate_norm_cache();
+        w->W.stream = stream;
+        return rc;
+    }
+    return PDWT_OK;
+}
+int pdwt_wavelets_invalidate_norm_cache(pdwt_wavelets* w)
+{
+    CHECK_W;
+    w->W.invalidate_norm_cache();
     return PDWT_OK;
 }
 int pdwt_wavelets_set_async(pdwt_wavelets* w, int on)

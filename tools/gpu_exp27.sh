@@ -1,0 +1,10 @@
+#!/bin/bash
+O=gpurun_out/exp27; mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log; tail -5 $O/pytest.log
+run() { timeout 120 env "$@" python tools/time_step.py $SHAPE 2>&1 | tail -1 | tee -a $O/times.txt; }
+for SHAPE in "4096 4096 1" "4096 4096 8" "2048 2048 64"; do
+  run PDWT_MULTI=0
+  run PDWT_MULTI=1
+  run PDWT_TH=64 PDWT_TM=32
+  run PDWT_TH=32 PDWT_TM=16
+done
