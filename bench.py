@@ -52,6 +52,19 @@ ROTATE = 4
 METRIC = "Mpixels/s fwd+inv 2D DWT db7 L3 4096^2"
 
 
+def config_of(workload):
+    """the `config` object of the JSON line: the same for both arms (the driver compares them)"""
+    Nr, Nc, wname, levels, nimg = WORKLOADS[workload]
+    npx = Nr * Nc * nimg
+    return {"workload": f"{workload}: {Nr}x{Nc} float32, {wname}, {levels} levels, separable DWT, "
+                        f"forward()+inverse() of {nimg} image(s) per GPU and step "
+                        f"(BASELINE.json configs[{1 if workload == 'c2' else 4}])",
+            "l2": (f"steps rotate over {ROTATE} Wavelets objects with distinct images/buffers (~1 GiB touched "
+                   f"between reuses, > 126 MB L2); no explicit flush") if nimg == 1 else
+                  f"one batched object of {nimg} images (inputs {4 * npx >> 20} MiB > 126 MB L2)",
+            "per_gpu": "every rank runs this workload on its own images; no data-path collective"}
+
+
 def seeded_image(shape, seed):
     return (np.random.default_rng(seed).standard_normal(shape) * 50 + 128).astype(np.float32)
 
@@ -120,7 +133,6 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = os.environ.get("PDWT_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -397,13 +409,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 1), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 5), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {Nr}x{Nc} float32, {wname}, {levels} levels, separable DWT, "
-                               f"forward()+inverse() of {nimg} image(s) per GPU and step "
-                               f"(BASELINE.json configs[{1 if args.workload == 'c2' else 4}])",
-                   "l2": (f"steps rotate over {ROTATE} Wavelets objects with distinct images/buffers (~1 GiB touched "
-                          f"between reuses, > 126 MB L2); no explicit flush") if nimg == 1 else
-                         f"one batched object of {nimg} images (inputs {4 * npx >> 20} MiB > 126 MB L2)",
-                   "per_gpu": "every rank runs this workload on its own images; no data-path collective"},
+        "config": config_of(args.workload),
         "e2e": {"value": round(e2e_val, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": 4 * npx,
                 "d2h_bytes_per_step": 4 * npx, "ms_per_step": round(ms_e2e / args.steps, 4),
                 "wall_ms_per_step": round(ms_e2e_wall / args.steps, 4),
@@ -425,7 +431,16 @@ def run_ours(args):
     if rank == 0 and world == 1 and args.workload == "c2":
         # north_star's target configuration ("batched 4096x4096 ... >= 70 % of HBM peak on 1 GPU"): the same transform
         # on 8 images held by ONE batched object, device-resident, same timing rules (inputs 512 MiB > L2)
-        out["batched_4096x8"] = batched_c2(L, peak, wname, levels, 8)
+        out["batched_4096x8"] = batched(L, peak, 4096, 4096, wname, levels, 8,
+                                        "8 x 4096x4096 float32 in one batched Wavelets object (north_star's target configuration)")
+    if rank == 0 and world == 1 and args.workload == "c2":
+        # the other BASELINE.json configurations, each with its own roofline and the reference's CUDA build beside it
+        out["configs"] = baseline_configs(L, peak)
+    if world > 1 and args.workload == "c2":
+        # BASELINE.json configs[4]: the batch sharded over the ranks THROUGH ShardedWavelets / Layer C over NCCL
+        sh = sharded_c5(world, rank, peak)
+        if rank == 0:
+            out["c5_sharded"] = sh
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_port_baseline(Nr, Nc, wname, levels, iters=3)
     if args.workload != "c2":
@@ -437,11 +452,10 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def batched_c2(L, peak, wname, levels, nimg, steps=10, warmup=3):
+def batched(L, peak, Nr, Nc, wname, levels, nimg, what, steps=10, warmup=3):
     import torch
     import pdwt_b200
     from pdwt_b200 import Wavelets
-    Nr = Nc = 4096
     x = torch.randn((nimg, Nr, Nc), device="cuda") * 50 + 128
     W = Wavelets(x, wname, levels)
     for _ in range(warmup):
@@ -461,7 +475,7 @@ def batched_c2(L, peak, wname, levels, nimg, steps=10, warmup=3):
     n = L.pdwt_profile_end(ents, 64)
     ks = {ents[k].name.decode(): 1e3 * ents[k].ms_total / ents[k].launches for k in range(max(n, 0))}
     npx = nimg * Nr * Nc
-    res = {"workload": f"{nimg} x 4096x4096 float32 in one batched Wavelets object, db7, {levels} levels, forward()+inverse()",
+    res = {"workload": f"{what}, {wname}, {levels} levels, forward()+inverse()",
            "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 4), "value": round(npx / (ms * 1e-3) / 1e6, 1),
            "unit": "Mpixels/s", "step_algorithmic_gbs": round(16.0 * npx / (ms * 1e-3) / 1e9, 1),
            "step_frac_of_peak": round(16.0 * npx / (ms * 1e-3) / 1e9 / peak, 4)}
@@ -476,6 +490,179 @@ def batched_c2(L, peak, wname, levels, nimg, steps=10, warmup=3):
     del W, x
     torch.cuda.empty_cache()
     return res
+
+
+def fp32_peak_tflops():
+    """148 SMs x 128 FP32 lanes x 2 flop x the maximum SM clock (MEASURED_PEAKS.json sm_max_mhz, else 1965 MHz)"""
+    mhz = 1965.0
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        mhz = float(json.load(open(p)).get("sm_max_mhz", mhz))
+    return 148 * 128 * 2 * mhz * 1e6 / 1e12
+
+
+def _timed_us(fn, iters, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / iters
+
+
+def _load_ref():
+    so = os.path.join(ROOT, "oracle", "_ref", "libpdwt_ref.so")
+    if not os.path.exists(so):
+        return None
+    try:
+        R = C.CDLL(so)
+    except OSError:
+        return None
+    fp = C.POINTER(C.c_float)
+    R.ref_create.restype = C.c_void_p
+    R.ref_create.argtypes = [fp, C.c_int, C.c_int, C.c_char_p] + [C.c_int] * 6
+    for n in ("ref_forward", "ref_inverse", "ref_destroy"):
+        getattr(R, n).argtypes = [C.c_void_p]
+    R.ref_soft_threshold.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
+    R.ref_norm1.argtypes = [C.c_void_p]
+    R.ref_norm1.restype = C.c_float
+    return R
+
+
+def baseline_configs(L, peak):
+    """BASELINE.json configs[2], [3] and (per GPU) [4], device-resident, CUDA events on the launching stream; the
+    reference's own CUDA build (oracle/_ref, same GPU, same inputs) beside each where it has a counterpart.
+    Algorithmic bytes and flops per pixel: SURVEY section 8d / DESIGN.md section 3.4."""
+    import torch
+    import pdwt_b200
+    from pdwt_b200 import Wavelets
+    R = _load_ref()
+    fp = C.POINTER(C.c_float)
+    tf = fp32_peak_tflops()
+    res = {}
+
+    def one(tag, shape, wname, levels, sep, swt, seq, iters, b_px, flop_px, what):
+        x = seeded_image(shape, 0)
+        npx = x.size
+        W = Wavelets(torch.from_numpy(x).cuda(), wname, levels, do_separable=sep, do_swt=swt)
+        l0 = L.pdwt_launch_count()
+        us = _timed_us(lambda: seq(W, None), iters)
+        launches = (L.pdwt_launch_count() - l0) // (iters + 3)
+        L.pdwt_profile_begin()
+        for _ in range(iters):
+            seq(W, None)
+        ents = (pdwt_b200.ProfileEntry * 64)()
+        n = L.pdwt_profile_end(ents, 64)
+        ks = {ents[k].name.decode(): round(1e3 * ents[k].ms_total / ents[k].launches * (ents[k].launches / iters), 2)
+              for k in range(max(n, 0))}
+        gbs, tfl = b_px * npx / us / 1e3, flop_px * npx / us / 1e6
+        d = {"workload": what, "steps": iters, "warmup": 3, "us_per_step": round(us, 1),
+             "value": round(npx / us, 1), "unit": "Mpixels/s", "gpu_launches_per_step": int(launches),
+             "roofline": {"hbm": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
+                                  "frac": round(gbs / peak, 4), "algorithmic_bytes_per_step": b_px * npx},
+                          "fp32": {"bound": "fp32 CUDA cores (no tensor cores: north_star)", "achieved": round(tfl, 2),
+                                   "peak": round(tf, 1), "unit": "TFLOP/s", "frac": round(tfl / tf, 4),
+                                   "algorithmic_flops_per_step": flop_px * npx}},
+             "us_per_step_by_kernel": ks}
+        d["roofline"]["binding"] = "fp32" if d["roofline"]["fp32"]["frac"] > d["roofline"]["hbm"]["frac"] else "hbm"
+        if R is not None:
+            h = R.ref_create(x.ctypes.data_as(fp), shape[0], shape[1], wname.encode(), levels, 1, sep, 0, swt, 2)
+            us_r = _timed_us(lambda: seq(None, h), max(3, iters // 2))
+            R.ref_destroy(h)
+            d["reference_cuda_us_per_step"] = round(us_r, 1)
+            d["vs_reference_cuda"] = round(us_r / us, 2)
+        del W
+        torch.cuda.empty_cache()
+        res[tag] = d
+
+    def seq_fwd_inv(W, h):
+        if W is not None:
+            W.forward(); W.inverse()
+        else:
+            R.ref_forward(h); R.ref_inverse(h)
+
+    def seq_c4(W, h):   # README.md:90-103
+        if W is not None:
+            W.forward(); W.norm1(); W.soft_threshold(10.0, 0, 0); W.norm1(); W.inverse()
+        else:
+            R.ref_forward(h); R.ref_norm1(h); R.ref_soft_threshold(h, 10.0, 0, 0); R.ref_norm1(h); R.ref_inverse(h)
+
+    try:
+        one("c3", (2048, 2048), "sym8", 4, 1, 1, seq_fwd_inv, 10, 112.0, 1536.0,
+            "configs[2]: 2-D SWT sym8, 4 levels, 2048x2048 float32, forward()+inverse()")
+        one("c4", (4096, 4096), "db7", 2, 0, 0, seq_c4, 6, 31.5, 980.0,
+            "configs[3]: non-separable 2-D DWT db7, 2 levels, 4096x4096 float32, forward -> norm1 -> "
+            "soft_threshold(10) -> norm1 -> inverse (README.md:90-103)")
+        res["c5_per_gpu"] = batched(L, peak, 2048, 2048, "db7", 3, 64,
+                                    "configs[4] per GPU: 64 of the 512 images of 2048x2048 in one batched object")
+    except Exception as e:   # extra blocks never take the headline line down
+        res["error"] = str(e)[:300]
+    return res
+
+
+def sharded_c5(world, rank, peak):
+    """BASELINE.json configs[4] at N GPUs: 64 x N images of 2048^2 (512 at N = 8), db7, 3 levels, held on rank 0's device,
+    scattered to the owners, transformed there, gathered back -- all through pdwt_b200.sharded.ShardedWavelets, i.e.
+    Layer C of the C ABI over NCCL (device to device).  Scatter, compute and gather are timed separately with CUDA
+    events (max over ranks); nothing here touches host memory."""
+    import torch
+    from pdwt_b200.sharded import ShardedWavelets
+    try:
+        Nr = Nc = 2048
+        per = 64
+        B = per * world
+        g = torch.Generator(device="cuda").manual_seed(11)
+        full = (torch.randn((B, Nr, Nc), device="cuda", generator=g) * 50 + 128) if rank == 0 else None
+        S = ShardedWavelets(full, "db7", 3)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def timed(fn, reps):
+            barrier(world)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            barrier(world)
+            return max_over_ranks(e0.elapsed_time(e1), world) / reps
+
+        for _ in range(2):
+            S.forward(); S.inverse()
+        ms_scatter = timed(lambda: S.scatter_batch(full), 3)
+        ms_compute = timed(lambda: (S.forward(), S.inverse()), 10)
+        dst = torch.empty_like(full) if rank == 0 else None
+        S.gather_image(out=dst)           # first use of the owners -> root direction sets the NCCL connections up
+        ms_gather = timed(lambda: S.gather_image(out=dst), 3)
+        rec = [dst]
+        err = None
+        if rank == 0:
+            err = float(((rec[0] - full).abs().max() / full.abs().max()).item())
+        S.forward()
+        n1 = S.norm1()
+        S.close()
+        npx = B * Nr * Nc
+        moved = 4.0 * (B - per) * Nr * Nc      # bytes that cross NVLink per direction (the root keeps its own block)
+        out = {"workload": f"configs[4]: {B} images of {Nr}x{Nc} float32, db7, 3 levels, {per} per GPU on {world} GPUs, "
+                           f"ShardedWavelets (Layer C: grouped ncclSend/ncclRecv, device to device)",
+               "scatter_ms": round(ms_scatter, 3), "compute_ms_per_step": round(ms_compute, 4), "gather_ms": round(ms_gather, 3),
+               "compute_only": {"value": round(npx / ms_compute / 1e3, 1), "unit": "Mpixels/s",
+                                "per_gpu_step_algorithmic_gbs": round(16.0 * per * Nr * Nc / ms_compute / 1e6, 1),
+                                "per_gpu_step_frac_of_peak": round(16.0 * per * Nr * Nc / ms_compute / 1e6 / peak, 4)},
+               "scatter_compute_gather": {"value": round(npx / (ms_scatter + ms_compute + ms_gather) / 1e3, 1),
+                                          "unit": "Mpixels/s"},
+               "root_link_gbs": {"scatter": round(moved / ms_scatter / 1e6, 1), "gather": round(moved / ms_gather / 1e6, 1),
+                                 "nominal_nvlink5_per_direction": 900.0},
+               "reconstruction_err": err, "norm1_of_first_and_last_image": [float(n1[0]), float(n1[-1])],
+               "nccl": "bound at run time by libpdwt_b200.so (dlopen libnccl.so.2)"}
+        del S, full
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:
+        return {"error": str(e)[:300]}
 
 
 def cpu_port_baseline(Nr, Nc, wname, levels, iters):
@@ -504,8 +691,7 @@ def run_reference(args):
     if nimg != 1:
         raise SystemExit("--impl reference: the reference has no batch dimension; use c2 or c5img")
     npx = Nr * Nc
-    cfg = {"workload": f"{args.workload}: {Nr}x{Nc} float32, {wname}, {levels} levels, separable DWT, "
-                       f"forward()+inverse() of one image per step (BASELINE.json configs[1])"}
+    cfg = config_of(args.workload)
     base = {"impl": "reference", "metric": METRIC, "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg}
@@ -564,7 +750,7 @@ def run_reference(args):
                                    "nvcc -arch=sm_100, oracle/_ref/libpdwt_ref.so) on the same B200 through the "
                                    "reference's own Wavelets class; every step, rotating over 4 objects"},
         "clocks": clk.summary(), "reconstruction_err": err,
-        "config": dict(cfg, l2=f"steps rotate over {ROTATE} reference Wavelets objects"),
+        "config": cfg,
     })
     print(json.dumps(base), flush=True)
 

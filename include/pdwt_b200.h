@@ -207,6 +207,36 @@ long long pdwt_launch_count(void);     /* process-wide */
 
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Layer C: a batch of independent planes spread over the GPUs of one node (the reference has no
+ * multi-GPU support, TODO.txt:15).  One process (or thread) per GPU; rank r of G owns a contiguous block of planes
+ * (pdwt_shard_block) as ONE batched pdwt_wavelets object, the transforms never communicate, and inputs / outputs
+ * move device to device over NCCL (NVLink): grouped ncclSend / ncclRecv from / to the root's device buffer, one
+ * ncclAllGather for per-plane norms.  NCCL is bound at run time (libnccl.so.2); without it these entry points
+ * return PDWT_ERR_CUDA and pdwt_shard_last_error() says why.  All pointers are DEVICE pointers unless noted.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct pdwt_shard pdwt_shard;
+int pdwt_shard_nccl_version(void);                 /* 0: no usable NCCL */
+const char* pdwt_shard_last_error(void);
+int pdwt_shard_unique_id(unsigned char id[128]);   /* ncclGetUniqueId on one rank; hand the bytes to the others */
+int pdwt_shard_create(pdwt_shard** out, const unsigned char id[128], int nranks, int rank); /* binds the current device */
+void pdwt_shard_destroy(pdwt_shard* s);
+int pdwt_shard_rank(const pdwt_shard* s);
+int pdwt_shard_nranks(const pdwt_shard* s);
+/* block of rank `rank`: contiguous, the first n % nranks ranks own one plane more */
+void pdwt_shard_block(long long n, int nranks, int rank, long long* first, long long* count);
+/* root's n planes of `plane` floats -> every rank's block, and back; enqueued on `stream` */
+int pdwt_shard_scatter(pdwt_shard* s, const float* d_full, float* d_mine, long long n, size_t plane, int root, void* stream);
+int pdwt_shard_gather(pdwt_shard* s, const float* d_mine, float* d_full, long long n, size_t plane, int root, void* stream);
+/* the same with this rank's block held by a batched object (batch == its plane count), on the object's stream:
+ * scatter into d_image (state becomes W_INIT like set_image), gather of d_image or of sub-band `num` (`plane` = the
+ * logical size from pdwt_coeff_dims; refused after inverse() like get_coeff, wt.cu:476-479) */
+int pdwt_shard_scatter_image(pdwt_shard* s, pdwt_wavelets* w, const float* d_full, long long n, size_t plane, int root);
+int pdwt_shard_gather_image(pdwt_shard* s, pdwt_wavelets* w, float* d_full, long long n, size_t plane, int root);
+int pdwt_shard_gather_coeff(pdwt_shard* s, pdwt_wavelets* w, int num, float* d_full, long long n, size_t plane, int root);
+/* per-plane norms of the WHOLE batch on every rank: h_all = HOST array of n floats; which = 1 norm1, 2 norm2sq */
+int pdwt_shard_norms(pdwt_shard* s, pdwt_wavelets* w, int which, float* h_all, long long n);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Per-kernel timing (measurement aid, no counterpart in the reference).  Between _begin and _end every kernel
  * launch of this library is bracketed by a CUDA-event pair on the stream it is launched on; _end synchronises,
  * aggregates by kernel tag (first-seen order) and returns the number of distinct tags (entries beyond

@@ -8,8 +8,8 @@
 
 #include <new>
 
-#include "../../include/wt.h"
 #include "pdwt_common.cuh"
+#include "pdwt_object.h"
 
 namespace pdwt {
 int norm_impl(float** c, pdwt_w_info w, int batch, int mode, float* out, cudaStream_t s, double* d_sums, double* h_sums);
@@ -624,15 +624,6 @@ void Wavelets::print_informations()
 }
 
 // ================================================================================================ Layer B
-struct pdwt_wavelets {
-    Wavelets W;
-    pdwt_wavelets(const float* img, int Nr, int Nc, const char* wname, int levels, int memisonhost, int sep, int cs,
-                  int swt, int ndim, int batch)
-        : W(const_cast<float*>(img), Nr, Nc, wname, levels, memisonhost, sep, cs, swt, ndim, batch)
-    {
-    }
-    explicit pdwt_wavelets(const Wavelets& o) : W(o) {}
-};
 
 extern "C" {
 

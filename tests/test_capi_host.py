@@ -94,3 +94,30 @@ def test_no_cpu_fallback_without_device():
     rc = L.pdwt_forward_separable(h, fake, ptrs, fake, w, 1, None)
     assert rc == pdwt_b200.PDWT_ERR_CUDA
     L.pdwt_filters_destroy(h)
+
+
+def test_filter_table_regenerates_from_the_reference_sources(tmp_path):
+    """the committed table is exactly what tools/gen_filter_bank.py makes of the reference's filters.cpp (build container
+    only: the GPU box has no /root/reference; there the live reference library checks the values, test_gpu_reference_fullsize)"""
+    if not os.path.exists("/root/reference/src/filters.cpp"):
+        pytest.skip("/root/reference is not available here")
+    import subprocess
+    import sys
+    out = tmp_path / "filter_bank.inc"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_filter_bank.py"), str(out)], cwd=ROOT,
+                          stdout=subprocess.DEVNULL)
+    assert out.read_bytes() == open(os.path.join(ROOT, "pdwt_b200", "csrc", "filter_bank.inc"), "rb").read()
+
+
+def test_shard_block_arithmetic_matches_the_python_partition():
+    """Layer C: contiguous blocks, the first n % world ranks own one plane more (pure arithmetic, no NCCL, no device)"""
+    from pdwt_b200.sharded import partition
+    L = pdwt_b200.lib()
+    L.pdwt_shard_block.argtypes = [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.pdwt_shard_block.restype = None
+    for n, world in ((512, 8), (5, 2), (2, 3), (7, 3), (1, 4), (100, 7), (0, 2)):
+        blocks = partition(n, world)
+        for r in range(world):
+            f, c = C.c_longlong(), C.c_longlong()
+            L.pdwt_shard_block(n, world, r, C.byref(f), C.byref(c))
+            assert (f.value, f.value + c.value) == blocks[r], (n, world, r)

@@ -28,6 +28,8 @@ if rank == 0:
         ok &= np.array_equal(c5[i].view(np.uint32), O.get_coeff(5).view(np.uint32))
         O.soft_threshold(10.0); O.inverse()
         ok &= np.array_equal(rec[i].view(np.uint32), O.get_image().view(np.uint32))
-    print(f"sharded NCCL check: world={world} B={B} blocks={partition(B, world)} -> {'OK (bit-exact vs oracle)' if ok else 'MISMATCH'}", flush=True)
+    print(f"sharded NCCL check (Layer C, device to device): world={world} B={B} blocks={partition(B, world)} native={S.native} "
+          f"-> {'OK (bit-exact vs oracle)' if ok else 'MISMATCH'}", flush=True)
+S.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
