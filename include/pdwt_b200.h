@@ -72,6 +72,12 @@ int pdwt_filters_create(pdwt_filters** out, const char* wname, int do_swt);
 int pdwt_filters_create_custom(pdwt_filters** out, int hlen, const float* dec_lo, const float* dec_hi,
                                const float* rec_lo, const float* rec_hi);
 void pdwt_filters_destroy(pdwt_filters* f);
+/* Custom 2-D quadruple of the non-separable drivers (w_set_filters_forward_nonseparable / _inverse_nonseparable,
+ * nonseparable.cu:86-106): four hlen x hlen filters, row-major, the reference's array layout; direction +1 forward,
+ * -1 inverse.  Each direction keeps its own quadruple (the reference shares ONE set of __constant__ symbols between
+ * both, so its last upload wins).  Without one the drivers use the outer products of the 1-D banks. */
+int pdwt_filters_set_2d(pdwt_filters* f, int direction, const float* ll, const float* lh, const float* hl, const float* hh);
+int pdwt_filters_has_2d(const pdwt_filters* f, int direction);
 int pdwt_filters_hlen(const pdwt_filters* f);
 /* copies the four 1-D banks (hlen floats each) to host arrays; any pointer may be NULL */
 int pdwt_filters_get(const pdwt_filters* f, float* dec_lo, float* dec_hi, float* rec_lo, float* rec_hi);
@@ -182,6 +188,11 @@ int pdwt_wavelets_set_coeff(pdwt_wavelets* w, const float* coeff, int num, int m
 int pdwt_wavelets_set_filters_forward(pdwt_wavelets* w, const char* name, unsigned len, const float* lo,
                                       const float* hi);            /* wt.cu:560 (separable mode) */
 int pdwt_wavelets_set_filters_inverse(pdwt_wavelets* w, const float* lo, const float* hi); /* wt.cu:585 */
+/* the same in non-separable mode: four len x len filters (A, H, V, D order of the reference = LL, LH, HL, HH) */
+int pdwt_wavelets_set_filters_forward_2d(pdwt_wavelets* w, const char* name, unsigned len, const float* f1, const float* f2,
+                                         const float* f3, const float* f4);
+int pdwt_wavelets_set_filters_inverse_2d(pdwt_wavelets* w, const float* f1, const float* f2, const float* f3,
+                                         const float* f4);
 int pdwt_wavelets_sync(pdwt_wavelets* w);                          /* cudaStreamSynchronize of the object's stream */
 int pdwt_wavelets_set_stream(pdwt_wavelets* w, void* stream);
 /* on != 0: get_image / set_image / get_coeff / set_coeff only enqueue their host<->device copies on the object's

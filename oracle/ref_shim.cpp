@@ -42,6 +42,15 @@ int ref_get_image(void* w, float* out) { return static_cast<Wavelets*>(w)->get_i
 int ref_get_coeff(void* w, float* out, int num) { return static_cast<Wavelets*>(w)->get_coeff(out, num); }
 void ref_set_image(void* w, float* img, int on_device) { static_cast<Wavelets*>(w)->set_image(img, on_device); }
 void ref_set_coeff(void* w, float* c, int num, int on_device) { static_cast<Wavelets*>(w)->set_coeff(c, num, on_device); }
+// custom filter banks, wt.cu:560-602 (separable: f3 = f4 = NULL; non-separable: four len x len filters)
+int ref_set_filters_forward(void* w, const char* name, unsigned len, float* f1, float* f2, float* f3, float* f4)
+{
+    return static_cast<Wavelets*>(w)->set_filters_forward(const_cast<char*>(name), len, f1, f2, f3, f4);
+}
+int ref_set_filters_inverse(void* w, float* f1, float* f2, float* f3, float* f4)
+{
+    return static_cast<Wavelets*>(w)->set_filters_inverse(f1, f2, f3, f4);
+}
 int ref_nlevels(void* w) { return static_cast<Wavelets*>(w)->winfos.nlevels; }
 int ref_hlen(void* w) { return static_cast<Wavelets*>(w)->winfos.hlen; }
 int ref_ndims(void* w) { return static_cast<Wavelets*>(w)->winfos.ndims; }

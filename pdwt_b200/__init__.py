@@ -117,6 +117,10 @@ def lib() -> C.CDLL:
     L.pdwt_wavelets_set_coeff.argtypes = [vp, vp, ci, ci]
     L.pdwt_wavelets_set_filters_forward.argtypes = [vp, C.c_char_p, C.c_uint, _fp, _fp]
     L.pdwt_wavelets_set_filters_inverse.argtypes = [vp, _fp, _fp]
+    L.pdwt_wavelets_set_filters_forward_2d.argtypes = [vp, C.c_char_p, C.c_uint, _fp, _fp, _fp, _fp]
+    L.pdwt_wavelets_set_filters_inverse_2d.argtypes = [vp, _fp, _fp, _fp, _fp]
+    L.pdwt_filters_set_2d.argtypes = [vp, ci, _fp, _fp, _fp, _fp]
+    L.pdwt_filters_has_2d.argtypes = [vp, ci]
     L.pdwt_wavelets_set_stream.argtypes = [vp, vp]
     L.pdwt_wavelets_set_async.argtypes = [vp, ci]
     L.pdwt_wavelets_invalidate_norm_cache.argtypes = [vp]
@@ -396,13 +400,20 @@ class Wavelets:
             a = np.ascontiguousarray(coeff, dtype=np.float32)
             _check(self._L.pdwt_wavelets_set_coeff(self._h, a.ctypes.data_as(C.c_void_p), num, 0), "set_coeff")
 
-    def set_filters_forward(self, name: str, lo, hi) -> int:
-        lo = np.ascontiguousarray(lo, dtype=np.float32)
-        hi = np.ascontiguousarray(hi, dtype=np.float32)
-        return self._L.pdwt_wavelets_set_filters_forward(self._h, name.encode(), len(lo), lo.ctypes.data_as(_fp),
-                                                         hi.ctypes.data_as(_fp))
+    def set_filters_forward(self, name: str, f1, f2, f3=None, f4=None) -> int:
+        """wt.cu:560-583.  Separable mode: the 1-D pair (lo, hi).  Non-separable mode: four len x len filters (the
+        reference's A, H, V, D order = LL, LH, HL, HH); returns the reference's codes (0, -1 too long, -2 missing 2-D
+        filters, -3 failed)."""
+        f = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in (f1, f2, f3, f4)]
+        if f[0].ndim == 2 or f[2] is not None or not self.do_separable:
+            p = [a.ctypes.data_as(_fp) if a is not None else None for a in f]
+            return self._L.pdwt_wavelets_set_filters_forward_2d(self._h, name.encode(), f[0].shape[0], *p)
+        return self._L.pdwt_wavelets_set_filters_forward(self._h, name.encode(), len(f[0]), f[0].ctypes.data_as(_fp),
+                                                         f[1].ctypes.data_as(_fp))
 
-    def set_filters_inverse(self, lo, hi) -> int:
-        lo = np.ascontiguousarray(lo, dtype=np.float32)
-        hi = np.ascontiguousarray(hi, dtype=np.float32)
-        return self._L.pdwt_wavelets_set_filters_inverse(self._h, lo.ctypes.data_as(_fp), hi.ctypes.data_as(_fp))
+    def set_filters_inverse(self, f1, f2, f3=None, f4=None) -> int:
+        f = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in (f1, f2, f3, f4)]
+        if f[0].ndim == 2 or f[2] is not None or not self.do_separable:
+            p = [a.ctypes.data_as(_fp) if a is not None else None for a in f]
+            return self._L.pdwt_wavelets_set_filters_inverse_2d(self._h, *p)
+        return self._L.pdwt_wavelets_set_filters_inverse(self._h, f[0].ctypes.data_as(_fp), f[1].ctypes.data_as(_fp))

@@ -21,6 +21,10 @@ struct pdwt_filters {
     Taps taps;
     char name[128];
     pdwt::StreamPlans* plans;   // queues + device counters of the cross-level launches made with this handle (lazy)
+    // custom 2-D filter quadruples of the non-separable mode, [0] forward / [1] inverse (wt.cu:560-602): host copy and
+    // device copy of 4 x hlen*hlen floats (LL, LH, HL, HH); NULL = outer products of the 1-D banks
+    float* h_k2d[2];
+    float* d_k2d[2];
 };
 
 namespace pdwt {
@@ -210,9 +214,46 @@ void pdwt_filters_destroy(pdwt_filters* f)
 {
     if (!f) return;
     if (f->plans) stream_plans_destroy(f->plans);
+    for (int d = 0; d < 2; d++) {
+        free(f->h_k2d[d]);
+        if (f->d_k2d[d]) cudaFree(f->d_k2d[d]);
+    }
     free(f);
 }
 int pdwt_filters_hlen(const pdwt_filters* f) { return f ? f->taps.hlen : PDWT_ERR_ARG; }
+
+// w_set_filters_forward_nonseparable / w_set_filters_inverse_nonseparable, nonseparable.cu:86-106: four hlen x hlen
+// filters (row-major, the reference's array layout) for one direction.  Unlike the reference, where both directions
+// share ONE set of __constant__ symbols (the last upload wins), each direction keeps its own quadruple.
+int pdwt_filters_set_2d(pdwt_filters* f, int direction, const float* ll, const float* lh, const float* hl, const float* hh)
+{
+    if (!f || (direction != 1 && direction != -1) || !ll || !lh || !hl || !hh) return PDWT_ERR_ARG;
+    const int d = direction > 0 ? 0 : 1, n = f->taps.hlen * f->taps.hlen;
+    if (n < 1) return PDWT_ERR_ARG;
+    float* h = (float*)malloc(sizeof(float) * 4 * n);
+    if (!h) return PDWT_ERR_ALLOC;
+    memcpy(h, ll, sizeof(float) * n);
+    memcpy(h + n, lh, sizeof(float) * n);
+    memcpy(h + 2 * n, hl, sizeof(float) * n);
+    memcpy(h + 3 * n, hh, sizeof(float) * n);
+    float* dv = nullptr;
+    cudaError_t e = cudaMalloc(&dv, sizeof(float) * 4 * n);
+    if (e == cudaSuccess) e = cudaMemcpy(dv, h, sizeof(float) * 4 * n, cudaMemcpyHostToDevice);   // blocking: visible to any stream
+    if (e != cudaSuccess) {
+        free(h);
+        if (dv) cudaFree(dv);
+        return note_cuda(e);
+    }
+    free(f->h_k2d[d]);
+    if (f->d_k2d[d]) cudaFree(f->d_k2d[d]);
+    f->h_k2d[d] = h;
+    f->d_k2d[d] = dv;
+    return PDWT_OK;
+}
+int pdwt_filters_has_2d(const pdwt_filters* f, int direction)
+{
+    return (f && (direction == 1 || direction == -1)) ? (f->d_k2d[direction > 0 ? 0 : 1] != nullptr) : 0;
+}
 int pdwt_filters_get(const pdwt_filters* f, float* dec_lo, float* dec_hi, float* rec_lo, float* rec_hi)
 {
     if (!f) return PDWT_ERR_ARG;
@@ -599,6 +640,23 @@ StreamPlans* plans_of(const pdwt_filters* f)
 
 }  // namespace
 
+// the taps a driver hands to its kernels: the non-separable drivers add the custom quadruple of their direction
+static Taps taps_for(const pdwt_filters* f, int direction)
+{
+    Taps t = f->taps;
+    t.k2d = t.hk2d = nullptr;
+    if (direction) {
+        t.k2d = f->d_k2d[direction > 0 ? 0 : 1];
+        t.hk2d = f->h_k2d[direction > 0 ? 0 : 1];
+    }
+    return t;
+}
+#define MAKE_CTX_NS(direction)                                                                \
+    TRY(check_args(f, d_image, d_coeffs, d_tmp, winfos, batch, true));                        \
+    const Taps taps_ns = taps_for(f, direction);                                              \
+    Ctx x{taps_ns, d_image, d_coeffs, d_tmp, winfos, batch, (cudaStream_t)stream,             \
+          (size_t)winfos.Nr * winfos.Nc, 2 * (size_t)winfos.Nr * winfos.Nc, plans_of(f)}
+
 #define MAKE_CTX(need_f)                                                                      \
     TRY(check_args(f, d_image, d_coeffs, d_tmp, winfos, batch, need_f));                      \
     Ctx x{(need_f) ? f->taps : kNoTaps, d_image, d_coeffs, d_tmp, winfos, batch, (cudaStream_t)stream, \
@@ -618,10 +676,10 @@ int pdwt_haar_forward2d(PDWT_DRIVER_ARGS) { MAKE_CTX(false); return fwd_single(x
 int pdwt_haar_inverse2d(PDWT_DRIVER_ARGS) { MAKE_CTX(false); return inv_single(x, HAAR2); }
 int pdwt_haar_forward1d(PDWT_DRIVER_ARGS) { MAKE_CTX(false); return fwd_single(x, HAAR1); }
 int pdwt_haar_inverse1d(PDWT_DRIVER_ARGS) { MAKE_CTX(false); return inv_single(x, HAAR1); }
-int pdwt_forward_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return fwd_single(x, NONSEP); }
-int pdwt_inverse_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return inv_single(x, NONSEP); }
-int pdwt_forward_swt_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return fwd_single(x, NONSEP_SWT); }
-int pdwt_inverse_swt_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX(true); return inv_single(x, NONSEP_SWT); }
+int pdwt_forward_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX_NS(1); return fwd_single(x, NONSEP); }
+int pdwt_inverse_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX_NS(-1); return inv_single(x, NONSEP); }
+int pdwt_forward_swt_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX_NS(1); return fwd_single(x, NONSEP_SWT); }
+int pdwt_inverse_swt_nonseparable(PDWT_DRIVER_ARGS) { MAKE_CTX_NS(-1); return inv_single(x, NONSEP_SWT); }
 
 // Wavelets::forward dispatch, wt.cu:247-266
 int pdwt_forward(PDWT_DRIVER_ARGS, int do_separable)

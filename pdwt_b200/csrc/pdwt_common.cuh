@@ -17,7 +17,15 @@ struct Taps {
     float H[PDWT_MAX_FILTER_WIDTH];   // analysis high-pass  (c_kern_H)
     float IL[PDWT_MAX_FILTER_WIDTH];  // synthesis low-pass  (c_kern_IL)
     float IH[PDWT_MAX_FILTER_WIDTH];  // synthesis high-pass (c_kern_IH)
+    // Non-separable mode with a CUSTOM filter quadruple (Wavelets::set_filters_forward/_inverse with four 2-D filters,
+    // wt.cu:560-602): 4 x hlen*hlen floats, (LL, LH, HL, HH) in the reference's array layout, for the direction of the
+    // driver that was called (device copy for the kernels, host copy for launchers that build parameter tables).
+    // NULL = the outer products of the 1-D banks (w_outer, nonseparable.cu:16-24).
+    const float* k2d;
+    const float* hk2d;
 };
+// filter f (0 LL, 1 LH, 2 HL, 3 HH) at reference index idx = row * hlen + col
+__host__ __device__ inline float k2d_at(const float* k2d, int hlen, int f, int idx) { return k2d[f * hlen * hlen + idx]; }
 
 // ---- index rules (reference lines cited at each use) ------------------------------------
 __host__ __device__ inline int half_up(int n) { return (n + 1) >> 1; }  // w_div2, utils.cu:24-27

@@ -407,10 +407,11 @@ __global__ void __launch_bounds__(GX* GY)
         for (int jx = 0; jx < hlen; jx++) {
             const float v = row[fold_dec(2 * gx - c + jx, Nc)];
             const float lx = t.L[hlen - 1 - jx], hx = t.H[hlen - 1 - jx];
-            ra = fmaf(v, __fmul_rn(ly, lx), ra);
-            rh = fmaf(v, __fmul_rn(ly, hx), rh);
-            rv = fmaf(v, __fmul_rn(hy, lx), rv);
-            rd = fmaf(v, __fmul_rn(hy, hx), rd);
+            const int ki = (hlen - 1 - jy) * hlen + (hlen - 1 - jx);   // nonseparable.cu:155-160
+            ra = fmaf(v, t.k2d ? k2d_at(t.k2d, hlen, 0, ki) : __fmul_rn(ly, lx), ra);
+            rh = fmaf(v, t.k2d ? k2d_at(t.k2d, hlen, 1, ki) : __fmul_rn(ly, hx), rh);
+            rv = fmaf(v, t.k2d ? k2d_at(t.k2d, hlen, 2, ki) : __fmul_rn(hy, lx), rv);
+            rd = fmaf(v, t.k2d ? k2d_at(t.k2d, hlen, 3, ki) : __fmul_rn(hy, hx), rd);
         }
     }
     const size_t o = (size_t)gy * nc + gx;
@@ -445,10 +446,11 @@ __global__ void __launch_bounds__(GX* GY)
             if (jx > Nc - 1 - hx + sg.c) x -= Nc;
             const float lx = t.IL[hlen - 1 - (2 * jx + ox)], hxv = t.IH[hlen - 1 - (2 * jx + ox)];
             const size_t i = (size_t)y * Nc + x;
-            ra = fmaf(pa[i], __fmul_rn(ly, lx), ra);
-            rh = fmaf(ph[i], __fmul_rn(ly, hxv), rh);
-            rv = fmaf(pv[i], __fmul_rn(hyv, lx), rv);
-            rd = fmaf(pd[i], __fmul_rn(hyv, hxv), rd);
+            const int ki = (hlen - 1 - (2 * jy + oy)) * hlen + (hlen - 1 - (2 * jx + ox));   // nonseparable.cu:216-219
+            ra = fmaf(pa[i], t.k2d ? k2d_at(t.k2d, hlen, 0, ki) : __fmul_rn(ly, lx), ra);
+            rh = fmaf(ph[i], t.k2d ? k2d_at(t.k2d, hlen, 1, ki) : __fmul_rn(ly, hxv), rh);
+            rv = fmaf(pv[i], t.k2d ? k2d_at(t.k2d, hlen, 2, ki) : __fmul_rn(hyv, lx), rv);
+            rd = fmaf(pd[i], t.k2d ? k2d_at(t.k2d, hlen, 3, ki) : __fmul_rn(hyv, hxv), rd);
         }
     }
     img[pz * s_img + (size_t)gy * Nc2 + gx] = __fadd_rn(__fadd_rn(__fadd_rn(ra, rh), rv), rd);
@@ -471,10 +473,11 @@ __global__ void __launch_bounds__(GX* GY)
         for (int jx = 0; jx < hlen; jx++) {
             const float v = row[fold_swt(gx, jx * fac, c, Nc)];
             const float lx = t.L[hlen - 1 - jx], hx = t.H[hlen - 1 - jx];
-            ra = fmaf(v, __fmul_rn(ly, lx), ra);
-            rh = fmaf(v, __fmul_rn(ly, hx), rh);
-            rv = fmaf(v, __fmul_rn(hy, lx), rv);
-            rd = fmaf(v, __fmul_rn(hy, hx), rd);
+            const int ki = (hlen - 1 - jy) * hlen + (hlen - 1 - jx);   // nonseparable.cu:339-342
+            ra = fmaf(v, t.k2d ? k2d_at(t.k2d, hlen, 0, ki) : __fmul_rn(ly, lx), ra);
+            rh = fmaf(v, t.k2d ? k2d_at(t.k2d, hlen, 1, ki) : __fmul_rn(ly, hx), rh);
+            rv = fmaf(v, t.k2d ? k2d_at(t.k2d, hlen, 2, ki) : __fmul_rn(hy, lx), rv);
+            rd = fmaf(v, t.k2d ? k2d_at(t.k2d, hlen, 3, ki) : __fmul_rn(hy, hx), rd);
         }
     }
     const size_t o = (size_t)gy * Nc + gx;
@@ -501,10 +504,11 @@ __global__ void __launch_bounds__(GX* GY)
         for (int jx = 0; jx < taps; jx++) {
             const size_t i = yo + fold_swt(gx, jx * fac, c, Nc);
             const float lx = t.IL[hlen - 1 - jx], hx = t.IH[hlen - 1 - jx];
-            ra = __fadd_rn(ra, __fmul_rn(pa[i], __fmul_rn(ly, lx)) * 0.25f);
-            rh = __fadd_rn(rh, __fmul_rn(ph[i], __fmul_rn(ly, hx)) * 0.25f);
-            rv = __fadd_rn(rv, __fmul_rn(pv[i], __fmul_rn(hy, lx)) * 0.25f);
-            rd = __fadd_rn(rd, __fmul_rn(pd[i], __fmul_rn(hy, hx)) * 0.25f);
+            const int ki = (hlen - 1 - jy) * hlen + (hlen - 1 - jx);   // nonseparable.cu:390-393
+            ra = __fadd_rn(ra, __fmul_rn(pa[i], t.k2d ? k2d_at(t.k2d, hlen, 0, ki) : __fmul_rn(ly, lx)) * 0.25f);
+            rh = __fadd_rn(rh, __fmul_rn(ph[i], t.k2d ? k2d_at(t.k2d, hlen, 1, ki) : __fmul_rn(ly, hx)) * 0.25f);
+            rv = __fadd_rn(rv, __fmul_rn(pv[i], t.k2d ? k2d_at(t.k2d, hlen, 2, ki) : __fmul_rn(hy, lx)) * 0.25f);
+            rd = __fadd_rn(rd, __fmul_rn(pd[i], t.k2d ? k2d_at(t.k2d, hlen, 3, ki) : __fmul_rn(hy, hx)) * 0.25f);
         }
     }
     img[pz * s_img + (size_t)gy * Nc + gx] = __fadd_rn(__fadd_rn(__fadd_rn(ra, rh), rv), rd);

@@ -72,7 +72,7 @@ struct NsFwdCfg {
     __host__ __device__ static constexpr int slot(int u) { return ((((u >> 2) & 1) * HALF + (u >> 3)) << 2) + (u & 3); }
 };
 
-// KC (opt-in, PDWT_NS_FWD_CONST=1; GPU parity bit-exact, not yet timed against the default side by side): the filter table arrives as a
+// KC (the default; PDWT_NS_FWD_CONST=0 switches it off): the filter table arrives as a
 // kernel parameter and is read through the uniform datapath like the inverse's (see NsInvK) instead of from shared memory.
 template <int HLEN>
 struct NsFwdK {
@@ -99,7 +99,10 @@ __global__ void __launch_bounds__(kNsThreads, 2)
         for (int i = tid; i < HLEN * HLEN; i += kNsThreads) {
             const int jy = i / HLEN, jx = i - jy * HLEN;
             const float ly = t.L[HLEN - 1 - jy], hy = t.H[HLEN - 1 - jy], lx = t.L[HLEN - 1 - jx], hx = t.H[HLEN - 1 - jx];
-            S_k[i] = make_float4(__fmul_rn(ly, lx), __fmul_rn(ly, hx), __fmul_rn(hy, lx), __fmul_rn(hy, hx));
+            const int ki = (HLEN - 1 - jy) * HLEN + (HLEN - 1 - jx);
+            S_k[i] = t.k2d ? make_float4(k2d_at(t.k2d, HLEN, 0, ki), k2d_at(t.k2d, HLEN, 1, ki), k2d_at(t.k2d, HLEN, 2, ki),
+                                         k2d_at(t.k2d, HLEN, 3, ki))   // a custom filter quadruple (wt.cu:560-583)
+                           : make_float4(__fmul_rn(ly, lx), __fmul_rn(ly, hx), __fmul_rn(hy, lx), __fmul_rn(hy, hx));
         }
     }
     pdl_wait();
@@ -346,8 +349,10 @@ static int launch_ns_fwd(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
     dim3 grid(idiv_up(half_up(Nc), K::TW), idiv_up(half_up(Nr), K::TH * rg), batch);
     if (grid.y > 65535u) return 0;
     PDWT_PROF(prof_tag("k_nonsep_fwd_tiled", Nr, Nc), s);
-    static const bool kconst = []() { const char* e = getenv("PDWT_NS_FWD_CONST"); return e && atoi(e) != 0; }();
-    if (kconst) {   // opt-in: the filter table as a kernel parameter (same products: one fp32 multiplication each)
+    // the filter table as a kernel parameter (uniform-datapath operands) is the default: C4 db7 377 -> 348 us on B200
+    // (PDWT_NS_FWD_CONST=0 forms the table in shared memory instead; a custom quadruple always does)
+    static const bool kconst = []() { const char* e = getenv("PDWT_NS_FWD_CONST"); return !e || atoi(e) != 0; }();
+    if (kconst && !t.k2d) {   // opt-in: the filter table as a kernel parameter (same products: one fp32 multiplication each)
         NsFwdK<HLEN> kt;
         for (int jy = 0; jy < HLEN; jy++)
             for (int jx = 0; jx < HLEN; jx++) {
@@ -397,6 +402,11 @@ static int launch_ns_inv(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V
                     const volatile float lx = t.IL[HLEN - 1 - (2 * jx + ox)], hx = t.IH[HLEN - 1 - (2 * jx + ox)];
                     volatile float ll = ly * lx, lh = ly * hx, hl = hy * lx, hh = hy * hx;   // no contraction, no excess precision
                     kt.k[ey][ex][jy][jx] = make_float4(ll, lh, hl, hh);
+                    if (t.hk2d) {   // a custom filter quadruple (wt.cu:585-602), reference indexing nonseparable.cu:216-219
+                        const int ki = (HLEN - 1 - (2 * jy + oy)) * HLEN + (HLEN - 1 - (2 * jx + ox));
+                        kt.k[ey][ex][jy][jx] = make_float4(k2d_at(t.hk2d, HLEN, 0, ki), k2d_at(t.hk2d, HLEN, 1, ki),
+                                                           k2d_at(t.hk2d, HLEN, 2, ki), k2d_at(t.hk2d, HLEN, 3, ki));
+                    }
                 }
     PDWT_PROF(prof_tag("k_nonsep_inv_tiled", Nr2, Nc2), s);
     PDWT_CUDA(launch_pdl(k_nonsep_inv_tiled<HLEN>, grid, kNsThreads, K::smem(rg), s, kt, img.p, img.stride, (const float*)A.p,

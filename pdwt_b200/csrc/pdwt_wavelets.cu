@@ -547,26 +547,36 @@ void Wavelets::set_coeff(DTYPE* coeff, int num, int mem_is_on_device)
     copy_coeff(this, coeff, num, mem_is_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, true);
 }
 
-// reference wt.cu:560-583 (separable mode; 2-D custom filters are a "next" row)
+// reference wt.cu:560-583.  Separable mode: the 1-D analysis pair.  Non-separable mode: four len x len filters
+// (nonseparable.cu:86-95); the object's 1-D banks are cleared, the quadruple of each direction lives in the handle.
 int Wavelets::set_filters_forward(char* filtername, unsigned int len, DTYPE* filter1, DTYPE* filter2, DTYPE* filter3,
                                   DTYPE* filter4)
 {
-    (void)filter3;
-    (void)filter4;
     if (len > PDWT_MAX_FILTER_WIDTH) {
         printf("ERROR: Wavelets.set_filters_forward(): filter length (%d) exceeds the maximum size (%d)\n", len,
                PDWT_MAX_FILTER_WIDTH);
         return -1;
     }
-    if (!do_separable) {
-        puts("ERROR: Wavelets.set_filters_forward(): custom 2-D (non-separable) filters are not provided by pdwt_b200");
+    if (!do_separable && (filter3 == NULL || filter4 == NULL)) {
+        puts("ERROR: Wavelets.set_filters_forward(): expected argument 4 and 5 for non-separable filtering");
         return -2;
     }
     if (!filter1 || !filter2 || len < 1) return -3;
-    float IL[PDWT_MAX_FILTER_WIDTH] = {0}, IH[PDWT_MAX_FILTER_WIDTH] = {0};
+    float Z[PDWT_MAX_FILTER_WIDTH] = {0};
     pdwt_filters* nf = NULL;
-    if (pdwt_filters_create_custom(&nf, (int)len, filter1, filter2, IL, IH) < 0) return -3;
-    if (filters) pdwt_filters_destroy(filters);
+    if (do_separable) {
+        if (pdwt_filters_create_custom(&nf, (int)len, filter1, filter2, Z, Z) < 0) return -3;
+    } else {
+        if (pdwt_filters_create_custom(&nf, (int)len, Z, Z, Z, Z) < 0) return -3;
+        if (pdwt_filters_set_2d(nf, 1, filter1, filter2, filter3, filter4) < 0) {
+            pdwt_filters_destroy(nf);
+            return -3;
+        }
+    }
+    if (filters) {
+        cudaStreamSynchronize((cudaStream_t)stream);   // kernels in flight may still read the old quadruple
+        pdwt_filters_destroy(filters);
+    }
     filters = nf;
     winfos.hlen = (int)len;
     if (filtername) {
@@ -579,14 +589,21 @@ int Wavelets::set_filters_forward(char* filtername, unsigned int len, DTYPE* fil
 // reference wt.cu:585-602: same length as the forward filters
 int Wavelets::set_filters_inverse(DTYPE* filter1, DTYPE* filter2, DTYPE* filter3, DTYPE* filter4)
 {
-    (void)filter3;
-    (void)filter4;
-    if (!do_separable) return -2;
+    if (!do_separable) {
+        if (filter3 == NULL || filter4 == NULL) {
+            puts("ERROR: Wavelets.set_filters_inverse(): expected argument 4 and 5 for non-separable filtering");
+            return -2;
+        }
+        if (!filters || !filter1 || !filter2) return -3;
+        cudaStreamSynchronize((cudaStream_t)stream);
+        return pdwt_filters_set_2d(filters, -1, filter1, filter2, filter3, filter4) < 0 ? -3 : 0;
+    }
     if (!filters || !filter1 || !filter2) return -3;
     float L[PDWT_MAX_FILTER_WIDTH], H[PDWT_MAX_FILTER_WIDTH];
     const int hlen = pdwt_filters_get(filters, L, H, NULL, NULL);
     pdwt_filters* nf = NULL;
     if (pdwt_filters_create_custom(&nf, hlen, L, H, filter1, filter2) < 0) return -3;
+    cudaStreamSynchronize((cudaStream_t)stream);
     pdwt_filters_destroy(filters);
     filters = nf;
     return 0;
@@ -741,6 +758,19 @@ int pdwt_wavelets_set_filters_inverse(pdwt_wavelets* w, const float* lo, const f
 {
     CHECK_W;
     return w->W.set_filters_inverse(const_cast<float*>(lo), const_cast<float*>(hi));
+}
+int pdwt_wavelets_set_filters_forward_2d(pdwt_wavelets* w, const char* name, unsigned len, const float* f1, const float* f2,
+                                         const float* f3, const float* f4)
+{
+    CHECK_W;
+    return w->W.set_filters_forward(const_cast<char*>(name), len, const_cast<float*>(f1), const_cast<float*>(f2),
+                                    const_cast<float*>(f3), const_cast<float*>(f4));
+}
+int pdwt_wavelets_set_filters_inverse_2d(pdwt_wavelets* w, const float* f1, const float* f2, const float* f3, const float* f4)
+{
+    CHECK_W;
+    return w->W.set_filters_inverse(const_cast<float*>(f1), const_cast<float*>(f2), const_cast<float*>(f3),
+                                    const_cast<float*>(f4));
 }
 int pdwt_wavelets_sync(pdwt_wavelets* w)
 {

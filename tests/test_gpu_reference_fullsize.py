@@ -205,3 +205,51 @@ def test_layer_a_with_caller_owned_buffers(ref, wname, levels, swt, shape):
     assert bitexact(d_image.cpu().numpy(), R.image())
     R.close()
     L.pdwt_filters_destroy(f)
+
+
+# --------------------------------------------------------------------- custom 2-D quadruples (non-separable mode)
+def _custom_cases():
+    import glob
+    return sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ns*2_custom_*.npz")))
+
+
+@pytest.mark.parametrize("path_", _custom_cases() or [None], ids=lambda p: os.path.basename(p)[:-4] if p else "none")
+def test_custom_2d_filter_quadruple_golden(path_):
+    """Wavelets::set_filters_forward/_inverse with four len x len filters (wt.cu:560-602, nonseparable.cu:86-106) against
+    vectors dumped from the reference's CUDA build (tests/golden/make_golden_custom2d.py)"""
+    if path_ is None:
+        pytest.skip("no custom-2-D golden vectors committed")
+    g = np.load(path_)
+    x, (levels, n) = g["x"], g["meta"]
+    swt = 1 if os.path.basename(path_).startswith("nsswt2") else 0
+    F, I = [g[f"F{j}"] for j in range(4)], [g[f"I{j}"] for j in range(4)]
+    for kpath in ("stream", "generic"):   # tiled kernels, then the generic ones
+        os.environ["PDWT_PATH"] = kpath
+        try:
+            W = Wavelets(x, "db%d" % (n // 2), int(levels), do_separable=0, do_swt=swt)
+            assert W.set_filters_forward("custom", *F) == 0
+            assert W.set_filters_inverse(*I) == 0      # both up front: each direction keeps its own quadruple here
+            W.forward()
+            for i in range(W.ncoeffs):
+                assert bitexact(W.get_coeff(i), g[f"c{i}"]), (kpath, i)
+            W.inverse()
+            assert bitexact(W.get_image(), g["recon"]), kpath
+        finally:
+            os.environ.pop("PDWT_PATH", None)
+
+
+def test_custom_2d_filter_quadruple_live_reference(ref):
+    from make_golden_custom2d import declare, quadruple, run_ref
+    declare(ref)
+    x = rnd((200, 264), 21)
+    n, levels = 10, 2
+    F, I = quadruple(n, 3), quadruple(n, 4)
+    r = run_ref(ref, x, n, levels, 0, F, I)
+    W = Wavelets(x, "db5", levels, do_separable=0)
+    assert W.set_filters_forward("mine", *F) == 0 and W.set_filters_inverse(*I) == 0
+    assert W.set_filters_forward("bad", F[0], F[1]) == -2      # the reference's code for missing 2-D filters
+    W.forward()
+    for i in range(W.ncoeffs):
+        assert bitexact(W.get_coeff(i), r[f"c{i}"]), i
+    W.inverse()
+    assert bitexact(W.get_image(), r["recon"])
