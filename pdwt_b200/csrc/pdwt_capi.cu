@@ -578,10 +578,16 @@ int fwd_single(const Ctx& x, Family fam)
                 Nr = half_up(Nr);
                 Nc = half_up(Nc);
                 break;
-            case NONSEP_SWT:
-                TRY(g_nonsep_swt_fwd(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
-                                     l + 1, x.batch, x.s));
+            case NONSEP_SWT: {
+                int done = 0;
+                if (path_cap() >= 1)
+                    TRY(done = n_nonsep_swt_fwd_level(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2),
+                                                      x.coeff(3 * l + 3), Nr, Nc, l + 1, x.batch, x.s));
+                if (!done)
+                    TRY(g_nonsep_swt_fwd(x.t, cur, dstA, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), Nr, Nc,
+                                         l + 1, x.batch, x.s));
                 break;
+            }
         }
         cur = dstA;
     }
@@ -614,10 +620,16 @@ int inv_single(const Ctx& x, Family fam)
                                      half_up(Mr), half_up(Mc), Mr, Mc, x.batch, x.s));
                 break;
             }
-            case NONSEP_SWT:
-                TRY(g_nonsep_swt_inv(x.t, dst, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), x.w.Nr,
-                                     x.w.Nc, l + 1, x.batch, x.s));
+            case NONSEP_SWT: {
+                int done = 0;
+                if (path_cap() >= 1)
+                    TRY(done = n_nonsep_swt_inv_level(x.t, dst, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2),
+                                                      x.coeff(3 * l + 3), x.w.Nr, x.w.Nc, l + 1, x.batch, x.s));
+                if (!done)
+                    TRY(g_nonsep_swt_inv(x.t, dst, cur, x.coeff(3 * l + 1), x.coeff(3 * l + 2), x.coeff(3 * l + 3), x.w.Nr,
+                                         x.w.Nc, l + 1, x.batch, x.s));
                 break;
+            }
         }
         cur = dst;
         cur_is_c0 = !cur_is_c0;

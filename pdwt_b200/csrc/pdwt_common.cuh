@@ -216,6 +216,12 @@ int n_nonsep_fwd_level(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, 
 int n_nonsep_inv_level(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int Nr2, int Nc2,
                        int batch, cudaStream_t s);
 
+// ---- register-tiled non-separable SWT level kernels, pdwt_nonsep_swt.cu: same convention (level = 1, 2, ...)
+int n_nonsep_swt_fwd_level(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int level,
+                           int batch, cudaStream_t s);
+int n_nonsep_swt_inv_level(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int level,
+                           int batch, cudaStream_t s);
+
 // ---- element-wise + reductions, pdwt_elementwise.cu ----------------------------------------------------------
 constexpr int kMaxSeg = 64;
 struct SegTable {  // list of (sub-band, length, parameter) handled by one launch
