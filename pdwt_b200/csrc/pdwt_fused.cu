@@ -29,6 +29,11 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -85,6 +90,16 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
             const int r = i / K::INW4, v = i - r * K::INW4;
             const int y = clampi(fold_dec(y_0 + r, Nr), 0, Nr - 1);
             cp_async16(S_in + r * K::INP + 4 * v, src + (size_t)y * Nc + x_al + 4 * v);
+        }
+        cp_async_wait_all();
+    } else if (x_al >= 0 && x_al + K::INW4 * 4 <= Nc) {
+        // rows that are not 16-byte aligned (Nc % 4 != 0: odd widths and their descendants) but a tile inside the plane:
+        // no column fold, 4-byte asynchronous copies, the whole tile in flight at once (the element-wise loop below
+        // made 4095 x 4097 five times slower than 4096 x 4096)
+        for (int i = tid; i < K::INR * (K::INW4 * 4); i += kFusedThreads) {
+            const int r = i / (K::INW4 * 4), j = i - r * (K::INW4 * 4);
+            const int y = clampi(fold_dec(y_0 + r, Nr), 0, Nr - 1);
+            cp_async4(S_in + r * K::INP + j, src + (size_t)y * Nc + x_al + j);
         }
         cp_async_wait_all();
     } else {
@@ -233,6 +248,17 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
             y -= (y >= nr) ? nr : 0;
             y = clampi(y, 0, nr - 1);
             cp_async16(S_c + (a * K::INR + r) * K::PW + 4 * v, srcs[a] + (size_t)y * nc + x_al + 4 * v);
+        }
+        cp_async_wait_all();
+    } else if (x_al >= 0 && x_al + K::INW4 * 4 <= nc) {   // unaligned rows, tile inside the plane: see the forward kernel
+        for (int i = tid; i < 4 * K::INR * (K::INW4 * 4); i += kFusedThreads) {
+            const int a = i / (K::INR * K::INW4 * 4), rem = i - a * (K::INR * K::INW4 * 4);
+            const int r = rem / (K::INW4 * 4), j = rem - r * (K::INW4 * 4);
+            int y = y_0 + r;
+            y += (y < 0) ? nr : 0;
+            y -= (y >= nr) ? nr : 0;
+            y = clampi(y, 0, nr - 1);
+            cp_async4(S_c + (a * K::INR + r) * K::PW + j, srcs[a] + (size_t)y * nc + x_al + j);
         }
         cp_async_wait_all();
     } else {

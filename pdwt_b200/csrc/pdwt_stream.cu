@@ -1369,7 +1369,7 @@ static int launch_inv_stream(const Taps& t, StreamPlans* plans, const StreamLeve
             int d = 0, per_sm = 0;
             cudaError_t e = cudaGetDevice(&d);
             if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(k_inv2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+                e = cudaFuncSetAttribute(k_inv2d_stream<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             if (e != cudaSuccess) return e;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv2d_stream<HLEN>, 32, G::SMEM) != cudaSuccess || per_sm < 1) {
                 cudaGetLastError();
@@ -1454,7 +1454,10 @@ static int launch_inv_stream(const Taps& t, StreamPlans* plans, const StreamLeve
     }
     if (nitems > 0x7fffffff) return 0;
     PDWT_PROF(prof_tag(n > 1 ? "k_inv2d_stream_levels" : "k_inv2d_stream", io[n - 1].Nr, io[n - 1].Nc), s);
-    cudaError_t e = launch_pdl(k_inv2d_stream<HLEN>, dim3((unsigned)nitems), 32, G::SMEM, s, p);
+    // PDWT_INV_SMEM_KB (experiments): pad the dynamic shared memory so that fewer one-warp CTAs share an SM
+    static const size_t smem_pad = []() { const char* e = getenv("PDWT_INV_SMEM_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
+    const size_t smem_bytes = smem_pad > G::SMEM && smem_pad <= 96 * 1024 ? smem_pad : G::SMEM;
+    cudaError_t e = launch_pdl(k_inv2d_stream<HLEN>, dim3((unsigned)nitems), 32, smem_bytes, s, p);
     if (e == cudaSuccess) {
         count_launch();
         e = cudaGetLastError();

@@ -78,6 +78,8 @@ ORACLE_CASES = [
     ((511, 512), "haar", 5, 1, 0, 2), ((16, 8191), "db4", 5, 1, 0, 1), ((7, 4096), "haar", 6, 1, 0, 1),
     ((256, 256), "sym8", 4, 1, 1, 2), ((100, 90), "db3", 3, 1, 1, 2), ((8, 1024), "db5", 4, 1, 1, 1),
     ((256, 256), "db7", 2, 0, 0, 2), ((97, 131), "sym4", 3, 0, 0, 2), ((64, 80), "db2", 2, 0, 1, 2),
+    # odd / unaligned widths large enough for interior tiles of the tile-fused kernels (4-byte asynchronous staging)
+    ((513, 1031), "db7", 3, 1, 0, 2), ((771, 1290), "sym8", 2, 1, 0, 2), ((640, 1026), "db2", 3, 1, 0, 2),
     # non-separable SWT through the tiled kernels (dilations 1, 2, 4, 8; odd sizes; a long filter)
     ((200, 264), "sym4", 3, 0, 1, 2), ((130, 96), "db7", 2, 0, 1, 2), ((97, 131), "db2", 4, 0, 1, 2),
     ((160, 192), "haar", 3, 0, 1, 2),

@@ -20,4 +20,13 @@ ncu --set full --clock-control none --import-source on -k regex:k_ -s 6 -c 6 -o 
 ncu --set full --clock-control none --import-source on -k regex:"k_reduce|k_threshold" -c 6 -o $O/ncu_elem python tools/prof_elem.py > $O/ncu_elem.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_swt|k_nonsep" -s 8 -c 16 -o $O/ncu_c3c4 python tools/prof_c3c4.py > $O/ncu_c3c4.log 2>&1
 for r in c2 b16 elem c3c4; do ncu -i $O/ncu_$r.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_summary.py > $O/ncu_${r}_summary.txt; done
+# per-launch DRAM bytes of the level-1 kernels at HEAD (bench.py -> roofline.traffic), then drop the big reports:
+# gpurun only brings back 64 MiB
+ncu -i $O/ncu_c2.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_traffic.py > $O/traffic.json
+for k in 0 5; do
+  ncu -i $O/ncu_b16.ncu-rep --page source --csv --print-source sass --launch-skip $k --launch-count 1 > $O/src_$k.csv 2>/dev/null
+  python tools/ncu_source_stalls.py $O/src_$k.csv 30 > $O/stalls_b16_$k.txt; rm -f $O/src_$k.csv
+done
+cuobjdump -sass -fun '_ZN4pdwt14k_fwd2d_streamILi14ELb1EEEvNS_9FwdParamsIXT_EEE' pdwt_b200/_build/pdwt_stream.o | grep -E "UTMALDG|SYNCS|LDGSTS|FFMA2" | sed 's#/\* 0x[0-9a-f]* \*/##' | awk '{c[$2]++} END{for(k in c) print k, c[k]}' > $O/sass_fwd_opcodes.txt
+rm -f $O/*.ncu-rep
 tail -3 $O/pytest_gpu.log; tail -2 $O/smoke.log; cut -c1-300 $O/bench_ref.json; cut -c1-300 $O/bench_ours.json; cat $O/sequence.txt | head -5
