@@ -48,7 +48,7 @@ WORKLOADS = {
     "c5": (2048, 2048, "db7", 3, 64),    # configs[4]: 512 images of 2048^2 over 8 GPUs = 64 per GPU, one batched object
     "c2b8": (4096, 4096, "db7", 3, 8),   # north_star's "batched 4096x4096": 8 images of configs[1] in one batched object
 }
-ROTATE = 4
+ROTATE = int(os.environ.get("PDWT_BENCH_ROTATE", "4"))
 METRIC = "Mpixels/s fwd+inv 2D DWT db7 L3 4096^2"
 
 
