@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libpdwt_b200.so")
-SOURCES = ["pdwt_generic.cu", "pdwt_elementwise.cu", "pdwt_fused.cu", "pdwt_stream.cu", "pdwt_swt.cu", "pdwt_nonsep.cu", "pdwt_nonsep_swt.cu", "pdwt_rows.cu", "pdwt_capi.cu", "pdwt_wavelets.cu", "pdwt_sharded.cu"]
+SOURCES = ["pdwt_generic.cu", "pdwt_elementwise.cu", "pdwt_fused.cu", "pdwt_stream.cu", "pdwt_swt.cu", "pdwt_nonsep.cu", "pdwt_nonsep_swt.cu", "pdwt_rows.cu", "pdwt_rows_all.cu", "pdwt_capi.cu", "pdwt_wavelets.cu", "pdwt_sharded.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
               "-fPIC,-O2,-Wall", "-Xptxas", "-v"] + (["-DPDWT_EXPERIMENTS"] if os.environ.get("PDWT_EXPERIMENTS") else [])
 

@@ -210,6 +210,11 @@ int r_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int n, i
 int r_swt_fwd_rows(const Taps& t, Plane2 img, Plane2 lo, Plane2 hi, int Nr, int Nc, int level, int batch, cudaStream_t s);
 int r_swt_inv_rows(const Taps& t, Plane2 t1, Plane2 t2, Plane2 img, int Nr, int Nc, int level, int batch, cudaStream_t s);
 
+// ---- all levels of a batched 1-D DWT in one launch (a row lives in shared memory), pdwt_rows_all.cu: same convention.
+// bands[0] = A_L, bands[l] = D_l (l = 1..L)
+int r_dwt1_fwd_all(const Taps& t, Plane2 img, const Plane2* bands, int Nr, int Nc, int L, int batch, cudaStream_t s);
+int r_dwt1_inv_all(const Taps& t, Plane2 img, const Plane2* bands, int Nr, int Nc, int L, int batch, cudaStream_t s);
+
 // ---- register-tiled non-separable DWT level kernels, pdwt_nonsep.cu: same convention
 int n_nonsep_fwd_level(const Taps& t, Plane2 img, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int batch,
                        cudaStream_t s);

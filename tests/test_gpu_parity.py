@@ -78,6 +78,9 @@ ORACLE_CASES = [
     ((511, 512), "haar", 5, 1, 0, 2), ((16, 8191), "db4", 5, 1, 0, 1), ((7, 4096), "haar", 6, 1, 0, 1),
     ((256, 256), "sym8", 4, 1, 1, 2), ((100, 90), "db3", 3, 1, 1, 2), ((8, 1024), "db5", 4, 1, 1, 1),
     ((256, 256), "db7", 2, 0, 0, 2), ((97, 131), "sym4", 3, 0, 0, 2), ((64, 80), "db2", 2, 0, 1, 2),
+    # batched 1-D transforms: all levels from one launch (a row in shared memory); long rows fall back to per-level kernels
+    ((64, 4096), "db7", 3, 1, 0, 1), ((33, 1001), "sym8", 4, 1, 0, 1), ((5, 12000), "db2", 6, 1, 0, 1),
+    ((3, 20000), "db3", 3, 1, 0, 1), ((40, 514), "db10", 2, 1, 0, 1),
     # odd / unaligned widths large enough for interior tiles of the tile-fused kernels (4-byte asynchronous staging)
     ((513, 1031), "db7", 3, 1, 0, 2), ((771, 1290), "sym8", 2, 1, 0, 2), ((640, 1026), "db2", 3, 1, 0, 2),
     # non-separable SWT through the tiled kernels (dilations 1, 2, 4, 8; odd sizes; a long filter)
