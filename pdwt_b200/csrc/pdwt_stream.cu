@@ -1178,7 +1178,11 @@ __global__ void __launch_bounds__(32, HLEN <= 14 ? 16 : 12) k_inv2d_stream(const
     const ptrdiff_t dH = (reinterpret_cast<const char*>(L.Hb) - reinterpret_cast<const char*>(L.A)) + 4 * plane_d;
     const ptrdiff_t dV = (reinterpret_cast<const char*>(L.V) - reinterpret_cast<const char*>(L.A)) + 4 * plane_d;
     const ptrdiff_t dD = (reinterpret_cast<const char*>(L.D) - reinterpret_cast<const char*>(L.A)) + 4 * plane_d;
-    const ptrdiff_t row_b = 4 * (ptrdiff_t)nc, wrap_b = 4 * (ptrdiff_t)nc * nr;
+    ptrdiff_t row_b = 4 * (ptrdiff_t)nc, wrap_b = 4 * (ptrdiff_t)nc * nr;
+    int nr_w = nr;
+    // opaque to ptxas: otherwise it re-derives these from the (dynamically indexed) level parameters in front of every
+    // coefficient row -- an LDC, two 64-bit multiplies and three selects per row pair
+    asm volatile("" : "+l"(row_b), "+l"(wrap_b), "+r"(nr_w));
 
     // Coefficient rows travel global -> shared -> registers.  Each lane prefetches ITS OWN two columns of A, H, V, D
     // DEPTH rows ahead with 8-byte cp.async copies into a private 32-byte cell per ring row, and later reads the same
@@ -1199,7 +1203,7 @@ __global__ void __launch_bounds__(32, HLEN <= 14 ? 16 : 12) k_inv2d_stream(const
             pa += row_b;
             if (--to_wrap == 0) {
                 pa -= wrap_b;
-                to_wrap = nr;
+                to_wrap = nr_w;
             }
         }
         cp_async_commit();
@@ -1242,8 +1246,10 @@ __global__ void __launch_bounds__(32, HLEN <= 14 ? 16 : 12) k_inv2d_stream(const
     float* out = L.dst + (size_t)plane * L.s_dst + (size_t)(2 * m0 + g) * Mc + px0;
     const bool st0 = row_lane && px0 + 4 <= Mc, st1 = row_lane && px0 + 8 <= Mc;
     // tile addressing (see InvGeom): the writer stores chunk `lane`, the reader loads chunks 2*lq + v
-    unsigned char* const tile_wr = smem_inv + 16 * ((lane >> 1) + (lane & 1) * G::ODD0);
-    const unsigned char* const tile_rd = smem_inv + g * G::TROWB + 16 * lq;
+    unsigned tile_wr_off = 16 * ((lane >> 1) + (lane & 1) * G::ODD0), tile_rd_off = g * G::TROWB + 16 * lq;
+    asm volatile("" : "+r"(tile_wr_off), "+r"(tile_rd_off));   // opaque: no re-derivation from the lane index per row pair
+    unsigned char* const tile_wr = smem_inv + tile_wr_off;
+    const unsigned char* const tile_rd = smem_inv + tile_rd_off;
 
     int s = 0;
     bool more = true;
@@ -1279,10 +1285,15 @@ __global__ void __launch_bounds__(32, HLEN <= 14 ? 16 : 12) k_inv2d_stream(const
                     sv = ffma2(wV[sl], kl, sv);
                     sd = ffma2(wD[sl], kh, sd);
                 }
-                float t1a, t1b, t2a, t2b;
-                unpack2(fadd2(sa, sh), t1a, t1b);
-                unpack2(fadd2(sv, sd), t2a, t2b);
-                *reinterpret_cast<float4*>(tile_wr + (buf * 2 + par) * G::TROWB) = make_float4(t1a, t2a, t1b, t2b);
+                // the two branch sums are added last (separable.cu:283-288).  Four scalar adds that write the tile vector's
+                // registers in place: a packed add would leave (t1a,t1b),(t2a,t2b) and need moves to interleave them
+                float a0, a1, h0, h1, v0, v1, d0, d1;
+                unpack2(sa, a0, a1);
+                unpack2(sh, h0, h1);
+                unpack2(sv, v0, v1);
+                unpack2(sd, d0, d1);
+                *reinterpret_cast<float4*>(tile_wr + (buf * 2 + par) * G::TROWB) =
+                    make_float4(__fadd_rn(a0, h0), __fadd_rn(v0, d0), __fadd_rn(a1, h1), __fadd_rn(v1, d1));
             }
             __syncwarp();
             // row synthesis, w_kern_inverse_pass2 (separable.cu:293-328): img = IL_x(t1) + IH_x(t2)
