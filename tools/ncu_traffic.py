@@ -8,12 +8,15 @@ def val(r, k):
     u = units[ix[k]]
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 out = {}
+big = {}
 for r in rows[2:]:
     name = r[ix['Kernel Name']].split('(')[0].replace('void ', '').split('<')[0].strip()
     grid = r[ix['Grid Size']]
     key = name
-    if key in out:
+    g = int(grid.strip("()").split(",")[0])
+    if key in out and g <= big.get(key, 0):   # the level-1 launch = the largest grid of that kernel
         continue
+    big[key] = g
     out[key] = int(val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum'))
     out[key + "_grid"] = grid
 try:
