@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
         const bool use_tm = L.use_tm != 0;
         // level > 0: the source was written by other CTAs of this launch (generic proxy); the item was only handed out
         // once those rows were complete (acquire in q_take, then the block barrier): order the TMA engine's reads behind it
-        if (level > 0) asm volatile("fence.proxy.async.global;" ::: "memory");
+        // (level 0 as well: its source was written by the previous kernel of the stream behind griddepcontrol.wait)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
         TL(2, lane == 0);   // dependencies satisfied
         // super-slot k of strip w -> ring slot k % NSS
         auto issue = [&](const int k, const int w) {
