@@ -21,6 +21,9 @@
 // Shapes the tiles cannot serve (odd hlen, hlen > 20, dilations whose halo does not fit in shared memory) return 0 and
 // the caller falls back to the generic two-pass kernels.
 #include "pdwt_common.cuh"
+#include <algorithm>
+#include <mutex>
+#include <vector>
 
 namespace pdwt {
 
@@ -74,6 +77,14 @@ __device__ __forceinline__ u64 sw_fadd2(u64 a, u64 b)
     u64 d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
+}
+
+__device__ __forceinline__ void sts_u64(unsigned addr, u64 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 lds_u64(unsigned addr)
+{
+    u64 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ int wrap1(int i, int N)   // fold_swt as a function of the unwrapped index, then clamped
@@ -389,6 +400,206 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
     }
 }
 
+// ======================================================================================== inverse, streaming
+// The tiled inverse above recomputes: its column pass covers the dilated halo of the row pass (TW + 15 f columns for
+// TW outputs: 1.9x at f = 8) and every tile restages hlen - 1 rows for its TH = 16 (another 1.9x of staging).  This
+// kernel removes the second factor and most of the first:
+//   * a thread owns ONE column of t1/t2 and walks down the rows of one residue class modulo f.  The hlen rows its
+//     column pass needs live in a REGISTER window of (A,H) and (V,D) pairs; the loop is unrolled hlen times so the
+//     window rotates through static register names (no moves) -- a new row costs 4 coalesced loads, not a restage;
+//   * the finished (t1, t2) pair goes to a double-buffered row in shared memory, one block barrier per row, and the row
+//     pass (taps f apart) reads it from there.  The CTA is as wide as the register file allows (up to 640 columns), so
+//     the halo of 15 f columns is a small share of it: 1.03x (f = 1) ... 1.23x (f = 8) of the column pass, none of the
+//     row pass.
+// Arithmetic and index folding are those of the tiled kernel (separable.cu:553-626), bit for bit.
+constexpr int kSwtStreamMaxThreads = 512;
+template <int HLEN, int F>
+__global__ void __launch_bounds__(kSwtStreamMaxThreads, 1)
+    k_swt_inv_stream(const __grid_constant__ SwtHalfTaps<HLEN> t, const float* __restrict__ A, size_t s_a,
+                     const float* __restrict__ H, const float* __restrict__ V, const float* __restrict__ D, size_t s_d,
+                     float* __restrict__ dst, size_t s_dst, int Nr, int Nc, int two, int ch)
+{
+    constexpr int C = HLEN / 2;
+    __shared__ u64 S_t[2][kSwtStreamMaxThreads + (HLEN - 1) * F];   // (t1, t2) of the current / next row; the tail is
+                                                                    // never written: threads that read it have no output
+    auto khalf = [&](const int j) { return sw_pack2(t.k[j].x, t.k[j].y); };
+    const u64 ones = sw_pack2(t.one.x, t.one.y);
+    const int tid = threadIdx.x;
+    const int ry = blockIdx.y % F, chunk = blockIdx.y / F;
+    const int gx0 = blockIdx.x * two;
+    const int m0 = chunk * ch;
+    const int m1 = min(m0 + ch, (Nr - ry + F - 1) / F);             // class rows [m0, m1) of this chunk are inside the image
+    const int xc = wrap1(gx0 - C * F + tid, Nc);                    // this thread's column of t1/t2
+    // the four source pointers walk down the class rows m0 - C, m0 - C + 1, ... (image rows f apart, folded back by Nr:
+    // the reference's single wrap for every row an output needs -- (hlen-1) f < Nr -- and in range for the two rows
+    // that are fetched ahead past the chunk's end)
+    int gy = ry + F * (m0 - C);
+    gy += (gy < 0) ? Nr : 0;
+    gy = min(max(gy, 0), Nr - 1);   // only chunks without rows (m0 >= m1) can still be outside
+    const size_t step_dn = (size_t)F * Nc, step_wrap = step_dn - (size_t)Nr * Nc;   // the second one modulo 2^64
+    const float* pA = A + (size_t)blockIdx.z * s_a + (size_t)gy * Nc + xc;
+    const float* pH = H + (size_t)blockIdx.z * s_d + (size_t)gy * Nc + xc;
+    const float* pV = V + (size_t)blockIdx.z * s_d + (size_t)gy * Nc + xc;
+    const float* pD = D + (size_t)blockIdx.z * s_d + (size_t)gy * Nc + xc;
+    auto next_row = [&]() {
+        gy += F;
+        const bool w = gy >= Nr;
+        gy -= w ? Nr : 0;
+        const size_t d = w ? step_wrap : step_dn;
+        pA += d; pH += d; pV += d; pD += d;
+    };
+    const bool has_out = tid < two && gx0 + tid < Nc;
+    float* out = dst + (size_t)blockIdx.z * s_dst + (size_t)(ry + F * m0) * Nc + gx0 + tid;
+    unsigned st_off = (unsigned)__cvta_generic_to_shared(&S_t[0][tid]);
+    asm volatile("" : "+r"(st_off));   // opaque: otherwise ptxas re-derives it from SR_TID in every unrolled step
+    constexpr unsigned kRowBytes = sizeof(S_t[0]);
+    pdl_wait();
+
+    // window slot s holds class row m - C + j of the current output row m, with s = (u + j) % HLEN at unrolled step u
+    u64 wAH[HLEN], wVD[HLEN];
+#pragma unroll
+    for (int j = 0; j < HLEN - 1; j++) {
+        wAH[j] = sw_pack2(__ldg(pA), __ldg(pH));
+        wVD[j] = sw_pack2(__ldg(pV), __ldg(pD));
+        next_row();
+    }
+    float la[2][4];   // landing registers: the rows of the next two steps are in flight while this one computes
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        la[i][0] = __ldg(pA); la[i][1] = __ldg(pH); la[i][2] = __ldg(pV); la[i][3] = __ldg(pD);
+        next_row();
+    }
+
+    // Step m: the column pass of class row m (into one shared row) and the row pass of class row m - 1 (out of the
+    // other one) are independent, so they sit in ONE basic block and ptxas interleaves them -- the shared-memory loads
+    // of the row pass are covered by the column pass's arithmetic.  One barrier per step.  The first step's row pass and
+    // the last step's column pass compute values nobody keeps (the store is predicated; the loads stay in range).
+    for (int mb = m0; mb <= m1; mb += HLEN) {
+#pragma unroll
+        for (int u = 0; u < HLEN; u++) {
+            const int m = mb + u;
+            if (m <= m1) {   // uniform over the CTA
+                wAH[(u + HLEN - 1) % HLEN] = sw_pack2(la[u & 1][0], la[u & 1][1]);
+                wVD[(u + HLEN - 1) % HLEN] = sw_pack2(la[u & 1][2], la[u & 1][3]);
+                la[u & 1][0] = __ldg(pA); la[u & 1][1] = __ldg(pH); la[u & 1][2] = __ldg(pV); la[u & 1][3] = __ldg(pD);
+                next_row();
+                if (m >= m1) pdl_launch_dependents();
+                // row pass of the previous step's row, w_kern_inverse_swt_pass2 (separable.cu:593-626)
+                const unsigned rd = st_off + ((u + 1) & 1) * kRowBytes;
+                u64 acc = 0ull;
+#pragma unroll
+                for (int j = 0; j < HLEN; j++) acc = sw_add2_exact(sw_fmul2(lds_u64(rd + j * F * 8), khalf(j)), ones, acc);
+                // column pass, w_kern_inverse_swt_pass1 (separable.cu:553-589)
+                u64 r1 = 0ull, r2 = 0ull;
+#pragma unroll
+                for (int j = 0; j < HLEN; j++) {
+                    r1 = sw_add2_exact(sw_fmul2(wAH[(u + j) % HLEN], khalf(j)), ones, r1);
+                    r2 = sw_add2_exact(sw_fmul2(wVD[(u + j) % HLEN], khalf(j)), ones, r2);
+                }
+                float a, b, c, d, a1, a2;
+                sw_unpack2(r1, a, b);
+                sw_unpack2(r2, c, d);
+                sts_u64(st_off + (u & 1) * kRowBytes, sw_pack2(__fadd_rn(a, b), __fadd_rn(c, d)));
+                sw_unpack2(acc, a1, a2);
+                if (has_out && m > m0) *out = __fadd_rn(a1, a2);
+                out += (m > m0) ? step_dn : 0;
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// Geometry of a streaming launch.  A CTA is `threads` columns wide (the last (hlen-1) f of them only feed the row pass
+// of the others) and walks `ch` rows of one residue class.  Both are chosen by a cost model of the whole grid: CTAs
+// that fit on an SM at 128 registers per thread, waves of CTAs, steps per CTA (plus a few for the window fill), cost
+// of a step proportional to the warps resident on the SM -- the kernel is bound by FP32 issue, so what matters is that
+// the LAST wave is as full as the others and that the halo share stays small.
+struct SwtStreamPlan {
+    int threads, two, ntiles, ch, nchunks;
+};
+static bool swt_stream_plan(int hlen, int Nr, int Nc, int f, int batch, SwtStreamPlan& sp)
+{
+    struct Key {
+        int hlen, Nr, Nc, f, batch, dev;
+        SwtStreamPlan sp;
+        bool ok;
+    };
+    static std::mutex mu;
+    static std::vector<Key> cache;
+    static const int env_cw = getenv("PDWT_SWT_CW") ? atoi(getenv("PDWT_SWT_CW")) : 0;
+    static const int env_ch = getenv("PDWT_SWT_CH") ? atoi(getenv("PDWT_SWT_CH")) : 0;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        dev = 0;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Key& k : cache)
+        if (k.hlen == hlen && k.Nr == Nr && k.Nc == Nc && k.f == f && k.batch == batch && k.dev == dev) {
+            sp = k.sp;
+            return k.ok;
+        }
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) {
+        cudaGetLastError();
+        sms = 148;
+    }
+    const int halo = (hlen - 1) * f, rpc = idiv_up(Nr, f);
+    double best = -1.0;
+    sp.threads = 0;
+    for (int cw = 64; cw <= kSwtStreamMaxThreads; cw += 32) {
+        if (env_cw && cw != env_cw) continue;
+        const int two = cw - halo;
+        if (two < 32 && two < Nc) continue;
+        if (two < 1) continue;
+        const int nt = idiv_up(Nc, two);
+        const int cps = std::min(4, 512 / cw);   // 65536 registers / (128 x cw)
+        const long long slots = (long long)sms * cps;
+        for (int n = 1; n <= rpc && n <= 1024; n++) {
+            int ch = idiv_up(rpc, n);
+            if (env_ch) ch = env_ch;
+            const int nch = idiv_up(rpc, ch);
+            if ((long long)f * nch > 65535) continue;
+            const long long ncta = (long long)nt * f * nch * batch;
+            const long long waves = (ncta + slots - 1) / slots;
+            // a wave that does not fill the machine leaves its CTAs the SM to themselves: they run faster
+            const double per_sm = waves > 1 ? (double)cps : std::min<double>(cps, (double)ncta / sms < 1.0 ? 1.0 : (double)ncta / sms);
+            const double cost = (double)waves * (ch + 6) * std::max(per_sm * cw / 32.0, 16.0);   // < 16 warps on an SM do not keep the FP32 pipe busy
+            if (best < 0 || cost < best * 0.999 || (cost <= best * 1.001 && cw > sp.threads)) {
+                best = cost;
+                sp.threads = cw;
+                sp.two = two;
+                sp.ntiles = nt;
+                sp.ch = ch;
+                sp.nchunks = nch;
+            }
+            if (env_ch) break;
+        }
+    }
+    const bool ok = sp.threads != 0;
+    if (cache.size() < 64) cache.push_back(Key{hlen, Nr, Nc, f, batch, dev, sp, ok});
+    return ok;
+}
+
+template <int HLEN, int F>
+static int launch_swt_inv_stream_f(const SwtHalfTaps<HLEN>& ht, Plane2 A, Plane2 H, Plane2 V, Plane2 D, Plane2 dst, int Nr,
+                                   int Nc, int batch, cudaStream_t s)
+{
+    SwtStreamPlan sp;
+    if (!swt_stream_plan(HLEN, Nr, Nc, F, batch, sp)) return 0;
+    dim3 grid(sp.ntiles, F * sp.nchunks, batch);
+    PDWT_PROF(prof_tag("k_swt_inv_stream", Nr, F), s);
+    PDWT_CUDA(launch_pdl(k_swt_inv_stream<HLEN, F>, grid, sp.threads, 0, s, ht, (const float*)A.p, A.stride,
+                         (const float*)H.p, (const float*)V.p, (const float*)D.p, H.stride, dst.p, dst.stride, Nr, Nc,
+                         sp.two, sp.ch));
+    PDWT_LAUNCH_CHECK();
+    return 1;
+}
+static bool swt_inv_stream_on()
+{
+    const char* e = getenv("PDWT_SWT_INV_STREAM");   // 0: the tiled kernels for every level
+    return !(e && e[0] == '0');
+}
+
 // ================================================================================================ launchers
 template <int HLEN>
 static int launch_swt_fwd(const Taps& t, Plane2 src, Plane2 A, Plane2 H, Plane2 V, Plane2 D, int Nr, int Nc, int level,
@@ -433,10 +644,22 @@ static int launch_swt_inv(const Taps& t, Plane2 A, Plane2 H, Plane2 V, Plane2 D,
     const int rows_per_class = idiv_up(Nr, f);
     dim3 grid(idiv_up(Nc, K::TW), f * idiv_up(rows_per_class, K::TH), batch);
     if (grid.y > 65535u) return 0;
-    PDWT_PROF(prof_tag("k_swt_inv_fused", Nr, f), s);
     SwtHalfTaps<HLEN> ht;
     for (int j = 0; j < HLEN; j++) ht.k[j] = make_float2(t.IL[HLEN - 1 - j] * 0.5f, t.IH[HLEN - 1 - j] * 0.5f);
     ht.one = make_float2(1.0f, 1.0f);
+    if constexpr (HLEN <= 16) {
+        if (f <= 8 && swt_inv_stream_on()) {
+            int done = 0;
+            switch (f) {
+                case 1: done = launch_swt_inv_stream_f<HLEN, 1>(ht, A, H, V, D, dst, Nr, Nc, batch, s); break;
+                case 2: done = launch_swt_inv_stream_f<HLEN, 2>(ht, A, H, V, D, dst, Nr, Nc, batch, s); break;
+                case 4: done = launch_swt_inv_stream_f<HLEN, 4>(ht, A, H, V, D, dst, Nr, Nc, batch, s); break;
+                default: done = launch_swt_inv_stream_f<HLEN, 8>(ht, A, H, V, D, dst, Nr, Nc, batch, s); break;
+            }
+            if (done) return done;
+        }
+    }
+    PDWT_PROF(prof_tag("k_swt_inv_fused", Nr, f), s);
 #define PDWT_SWT_INV(FF)                                                                                                 \
     do {                                                                                                                 \
         PDWT_ONCE_PER_DEVICE(cudaFuncSetAttribute(k_swt_inv_fused<HLEN, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

@@ -86,6 +86,10 @@ ORACLE_CASES = [
     # non-separable SWT through the tiled kernels (dilations 1, 2, 4, 8; odd sizes; a long filter)
     ((200, 264), "sym4", 3, 0, 1, 2), ((130, 96), "db7", 2, 0, 1, 2), ((97, 131), "db2", 4, 0, 1, 2),
     ((160, 192), "haar", 3, 0, 1, 2),
+    # separable SWT, streaming inverse: several column tiles and row chunks, sizes that are no multiple of the dilation,
+    # a dilation whose halo is wider than a short image allows (falls back), short filters
+    ((300, 1100), "sym8", 4, 1, 1, 2), ((1000, 700), "db3", 3, 1, 1, 2), ((523, 1301), "db5", 4, 1, 1, 2),
+    ((96, 2050), "haar", 4, 1, 1, 2), ((2049, 130), "coif2", 3, 1, 1, 2),
 ]
 
 

@@ -1,6 +1,6 @@
 """Randomised parity sweep on the GPU: random shapes (odd, tiny, wide, tall), wavelets, level counts and transform
 modes through the public class, every sub-band / reconstruction / proximal result compared BIT FOR BIT with the CPU
-oracle.  usage: fuzz_gpu.py [cases] [seed]   (exit code 1 and the failing case on the first mismatch)"""
+oracle.  usage: [PDWT_FUZZ_MODE=swt2] [PDWT_FUZZ_HI=1500] fuzz_gpu.py [cases] [seed]   (exit code 1 and the failing case on the first mismatch)"""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, ".")
@@ -14,11 +14,15 @@ bitexact = lambda a, b: a.shape == b.shape and np.array_equal(a.view(np.uint32),
 t0, bad, ran = time.time(), 0, 0
 for it in range(n_cases):
     mode = rng.choice(["dwt2", "dwt2", "dwt2", "swt2", "ns2", "nsswt2", "dwt1", "swt1"])
+    if os.environ.get("PDWT_FUZZ_MODE"):     # one transform family only
+        mode = os.environ["PDWT_FUZZ_MODE"]
     wname = names[rng.integers(len(names))]
     if mode in ("ns2", "nsswt2") and rng.random() < 0.7:
         wname = rng.choice(["db2", "db3", "db4", "sym4", "db7", "coif2", "haar"])
     small = rng.random() < 0.35
     hi = 96 if small else (260 if mode in ("ns2", "nsswt2", "swt2") else 700)
+    if os.environ.get("PDWT_FUZZ_HI") and not small:   # larger planes: several column tiles / row chunks per level
+        hi = int(os.environ["PDWT_FUZZ_HI"])
     Nr = int(rng.integers(1 if mode.endswith("1") else 8, hi))
     Nc = int(rng.integers(8, hi * (3 if mode.endswith("1") else 1)))
     if rng.random() < 0.5:
