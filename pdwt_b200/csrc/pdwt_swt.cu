@@ -20,6 +20,8 @@
 // (separable.cu:575-588, 615-625).  Index folding is the reference's single +-N wrap (separable.cu:428-433).
 // Shapes the tiles cannot serve (odd hlen, hlen > 20, dilations whose halo does not fit in shared memory) return 0 and
 // the caller falls back to the generic two-pass kernels.
+// The inverse of the common shapes (hlen <= 16, dilation <= 8) runs k_swt_inv_stream further down instead: a register
+// window per column walks down the rows, nothing is restaged or recomputed (C3: 272 -> 223 us for the four levels).
 #include "pdwt_common.cuh"
 #include <algorithm>
 #include <mutex>
@@ -436,37 +438,42 @@ __global__ void __launch_bounds__(kSwtStreamMaxThreads, 1)
     int gy = ry + F * (m0 - C);
     gy += (gy < 0) ? Nr : 0;
     gy = min(max(gy, 0), Nr - 1);   // only chunks without rows (m0 >= m1) can still be outside
-    const size_t step_dn = (size_t)F * Nc, step_wrap = step_dn - (size_t)Nr * Nc;   // the second one modulo 2^64
-    const float* pA = A + (size_t)blockIdx.z * s_a + (size_t)gy * Nc + xc;
-    const float* pH = H + (size_t)blockIdx.z * s_d + (size_t)gy * Nc + xc;
-    const float* pV = V + (size_t)blockIdx.z * s_d + (size_t)gy * Nc + xc;
-    const float* pD = D + (size_t)blockIdx.z * s_d + (size_t)gy * Nc + xc;
+    // one 32-bit element offset serves the four planes (uniform base pointers): Nr * Nc < 2^31 is checked by the launcher
+    const float* bA = A + (size_t)blockIdx.z * s_a;
+    const float* bH = H + (size_t)blockIdx.z * s_d;
+    const float* bV = V + (size_t)blockIdx.z * s_d;
+    const float* bD = D + (size_t)blockIdx.z * s_d;
+    asm volatile("" : "+l"(bA), "+l"(bH), "+l"(bV), "+l"(bD));   // keep them: ptxas otherwise redoes blockIdx.z * stride in every step
+    const unsigned step_dn = (unsigned)F * (unsigned)Nc, plane_n = (unsigned)Nr * (unsigned)Nc;
+    unsigned off = (unsigned)gy * (unsigned)Nc + (unsigned)xc;
     auto next_row = [&]() {
         gy += F;
+        off += step_dn;
         const bool w = gy >= Nr;
         gy -= w ? Nr : 0;
-        const size_t d = w ? step_wrap : step_dn;
-        pA += d; pH += d; pV += d; pD += d;
+        off -= w ? plane_n : 0u;
     };
     const bool has_out = tid < two && gx0 + tid < Nc;
-    float* out = dst + (size_t)blockIdx.z * s_dst + (size_t)(ry + F * m0) * Nc + gx0 + tid;
+    // row pass output of step m is class row m - 1: the offset starts one row early (never stored through)
+    float* bO = dst + (size_t)blockIdx.z * s_dst;
+    asm volatile("" : "+l"(bO));
+    unsigned oo = (unsigned)(ry + F * m0) * (unsigned)Nc + (unsigned)(gx0 + tid) - step_dn;
     unsigned st_off = (unsigned)__cvta_generic_to_shared(&S_t[0][tid]);
     asm volatile("" : "+r"(st_off));   // opaque: otherwise ptxas re-derives it from SR_TID in every unrolled step
     constexpr unsigned kRowBytes = sizeof(S_t[0]);
     pdl_wait();
 
-    // window slot s holds class row m - C + j of the current output row m, with s = (u + j) % HLEN at unrolled step u
+    // window slot s holds class row m - C + j of the current output row m, with s = (u + j) % HLEN at unrolled step u.
+    // The slot of tap 0 is free as soon as that tap is done -- the first thing a step does -- and it is the slot of the
+    // next step's LAST tap: the loads of the next row go straight into it and have almost two steps to arrive.
+    // (Measured on C3: landing registers that keep 1, 2 or 4 rows in flight, an L2 prefetch 8 rows ahead and a
+    // shared-memory ring fed by LDGSTS all run at the same speed or slower; so does the kernel without its barrier.
+    // It is bound by FP32 issue -- 96 two-cycle packed instructions per row and thread plus ~55 others.)
     u64 wAH[HLEN], wVD[HLEN];
 #pragma unroll
-    for (int j = 0; j < HLEN - 1; j++) {
-        wAH[j] = sw_pack2(__ldg(pA), __ldg(pH));
-        wVD[j] = sw_pack2(__ldg(pV), __ldg(pD));
-        next_row();
-    }
-    float la[2][4];   // landing registers: the rows of the next two steps are in flight while this one computes
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        la[i][0] = __ldg(pA); la[i][1] = __ldg(pH); la[i][2] = __ldg(pV); la[i][3] = __ldg(pD);
+    for (int j = 0; j < HLEN; j++) {
+        wAH[j] = sw_pack2(__ldg(bA + off), __ldg(bH + off));
+        wVD[j] = sw_pack2(__ldg(bV + off), __ldg(bD + off));
         next_row();
     }
 
@@ -479,10 +486,6 @@ __global__ void __launch_bounds__(kSwtStreamMaxThreads, 1)
         for (int u = 0; u < HLEN; u++) {
             const int m = mb + u;
             if (m <= m1) {   // uniform over the CTA
-                wAH[(u + HLEN - 1) % HLEN] = sw_pack2(la[u & 1][0], la[u & 1][1]);
-                wVD[(u + HLEN - 1) % HLEN] = sw_pack2(la[u & 1][2], la[u & 1][3]);
-                la[u & 1][0] = __ldg(pA); la[u & 1][1] = __ldg(pH); la[u & 1][2] = __ldg(pV); la[u & 1][3] = __ldg(pD);
-                next_row();
                 if (m >= m1) pdl_launch_dependents();
                 // row pass of the previous step's row, w_kern_inverse_swt_pass2 (separable.cu:593-626)
                 const unsigned rd = st_off + ((u + 1) & 1) * kRowBytes;
@@ -490,9 +493,13 @@ __global__ void __launch_bounds__(kSwtStreamMaxThreads, 1)
 #pragma unroll
                 for (int j = 0; j < HLEN; j++) acc = sw_add2_exact(sw_fmul2(lds_u64(rd + j * F * 8), khalf(j)), ones, acc);
                 // column pass, w_kern_inverse_swt_pass1 (separable.cu:553-589)
-                u64 r1 = 0ull, r2 = 0ull;
+                u64 r1 = sw_add2_exact(sw_fmul2(wAH[u % HLEN], khalf(0)), ones, 0ull);
+                u64 r2 = sw_add2_exact(sw_fmul2(wVD[u % HLEN], khalf(0)), ones, 0ull);
+                wAH[u % HLEN] = sw_pack2(__ldg(bA + off), __ldg(bH + off));
+                wVD[u % HLEN] = sw_pack2(__ldg(bV + off), __ldg(bD + off));
+                next_row();
 #pragma unroll
-                for (int j = 0; j < HLEN; j++) {
+                for (int j = 1; j < HLEN; j++) {
                     r1 = sw_add2_exact(sw_fmul2(wAH[(u + j) % HLEN], khalf(j)), ones, r1);
                     r2 = sw_add2_exact(sw_fmul2(wVD[(u + j) % HLEN], khalf(j)), ones, r2);
                 }
@@ -501,8 +508,8 @@ __global__ void __launch_bounds__(kSwtStreamMaxThreads, 1)
                 sw_unpack2(r2, c, d);
                 sts_u64(st_off + (u & 1) * kRowBytes, sw_pack2(__fadd_rn(a, b), __fadd_rn(c, d)));
                 sw_unpack2(acc, a1, a2);
-                if (has_out && m > m0) *out = __fadd_rn(a1, a2);
-                out += (m > m0) ? step_dn : 0;
+                if (has_out && m > m0) bO[oo] = __fadd_rn(a1, a2);
+                oo += step_dn;
                 __syncthreads();
             }
         }
@@ -546,13 +553,15 @@ static bool swt_stream_plan(int hlen, int Nr, int Nc, int f, int batch, SwtStrea
     const int halo = (hlen - 1) * f, rpc = idiv_up(Nr, f);
     double best = -1.0;
     sp.threads = 0;
-    for (int cw = 64; cw <= kSwtStreamMaxThreads; cw += 32) {
+    const int max_thr = kSwtStreamMaxThreads, thr_per_sm = 512;   // 65536 registers / 128 per thread
+    const double extra = 6.0;                                      // window fill and launch, in steps
+    for (int cw = 64; cw <= max_thr; cw += 32) {
         if (env_cw && cw != env_cw) continue;
         const int two = cw - halo;
         if (two < 32 && two < Nc) continue;
         if (two < 1) continue;
         const int nt = idiv_up(Nc, two);
-        const int cps = std::min(4, 512 / cw);   // 65536 registers / (128 x cw)
+        const int cps = std::min(4, thr_per_sm / cw);   // 65536 registers / (registers per thread x cw)
         const long long slots = (long long)sms * cps;
         for (int n = 1; n <= rpc && n <= 1024; n++) {
             int ch = idiv_up(rpc, n);
@@ -563,7 +572,7 @@ static bool swt_stream_plan(int hlen, int Nr, int Nc, int f, int batch, SwtStrea
             const long long waves = (ncta + slots - 1) / slots;
             // a wave that does not fill the machine leaves its CTAs the SM to themselves: they run faster
             const double per_sm = waves > 1 ? (double)cps : std::min<double>(cps, (double)ncta / sms < 1.0 ? 1.0 : (double)ncta / sms);
-            const double cost = (double)waves * (ch + 6) * std::max(per_sm * cw / 32.0, 16.0);   // < 16 warps on an SM do not keep the FP32 pipe busy
+            const double cost = (double)waves * (ch + extra) * std::max(per_sm * cw / 32.0, 16.0);   // < 16 warps on an SM do not keep the FP32 pipe busy
             if (best < 0 || cost < best * 0.999 || (cost <= best * 1.001 && cw > sp.threads)) {
                 best = cost;
                 sp.threads = cw;
@@ -585,7 +594,7 @@ static int launch_swt_inv_stream_f(const SwtHalfTaps<HLEN>& ht, Plane2 A, Plane2
                                    int Nc, int batch, cudaStream_t s)
 {
     SwtStreamPlan sp;
-    if (!swt_stream_plan(HLEN, Nr, Nc, F, batch, sp)) return 0;
+    if ((long long)Nr * Nc >= (1ll << 31) || !swt_stream_plan(HLEN, Nr, Nc, F, batch, sp)) return 0;   // 32-bit offsets in the kernel
     dim3 grid(sp.ntiles, F * sp.nchunks, batch);
     PDWT_PROF(prof_tag("k_swt_inv_stream", Nr, F), s);
     PDWT_CUDA(launch_pdl(k_swt_inv_stream<HLEN, F>, grid, sp.threads, 0, s, ht, (const float*)A.p, A.stride,
