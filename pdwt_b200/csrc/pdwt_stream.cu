@@ -869,6 +869,18 @@ static bool multi_level_on()
     return e && atoi(e) != 0;
 }
 
+// The inverse level kernel with a producer warp and a tensor-map ring (k_inv2d_tma) against the one whose arithmetic warps
+// stage their own rows (k_inv2d_stream).  Measured on B200 (tools/time_inv_variants.py, db7, level 1): the TMA variant wins
+// 5-7 % once the launch covers the machine several times over with large planes (8 x 4096^2: 203.9 against 214.6 us;
+// 64 x 2048^2: 404.6 against 433.3; 8 x 2048^2: 64.2 against 67.7) and loses on one or two 4096^2 planes (37.2 against
+// 35.3 us, 63.8 against 60.6) and on small planes whatever the batch (64 x 1024^2: 147.7 against 123.6 -- a larger
+// share of edge super-slots, which the producer stages in 8-byte pieces).  PDWT_INV_TMA=0|1 (read per call) overrides.
+static bool inv_tma_wanted(long long plane_px, int batch)
+{
+    if (const char* e = getenv("PDWT_INV_TMA")) return atoi(e) != 0;
+    return plane_px >= (1ll << 22) && plane_px * batch >= (1ll << 25);
+}
+
 // largest power of two <= 16 that divides a and b
 static int pow2_div(int a, int b)
 {
@@ -1330,6 +1342,296 @@ __global__ void __launch_bounds__(32, HLEN <= 14 ? 16 : 12) k_inv2d_stream(const
     if (p.q.items && L.q.signals) q_signal(p.q, L.q, plane, 2 * m0, 2 * nm);
 }
 
+// ---- the inverse level kernel with a TMA-fed ring (one level per launch) ---------------------------------------------------
+// Same arithmetic and the same consumer code as k_inv2d_stream, but the coefficient rows reach shared memory the way the
+// forward's input rows do: CTA = NCW consumer warps + ONE producer warp; a consumer owns a strip of 64 coefficient columns
+// and a private ring of NSS super-slots x SR rows x 4 planes (A, H, V, D); interior super-slots are FOUR tensor-map
+// requests (box 64 x SR per plane), edge super-slots (periodic wrap in rows or columns, separable.cu:265-273) are staged by
+// the producer's lanes with 8-byte LDGSTS pieces that arrive on the same "full" mbarrier.  The arithmetic warps issue no
+// global loads at all: 2368 one-warp CTAs reading four planes in 256-byte pieces (9 500 concurrent DRAM streams) become
+// 8-row boxes, and the per-lane LDGSTS + cp.async group accounting leaves the consumers' instruction stream.
+template <int HLEN>
+struct InvTmaGeom {
+    using G = InvGeom<HLEN>;
+    static constexpr int NCW = 4;                        // consumer warps per CTA
+    static constexpr int SR = (G::UNR % 4 == 0) ? 4 : 2; // coefficient rows per super-slot (static row index in the body)
+    static constexpr int NSS = 16 / SR;                  // super-slots per consumer ring (16 rows = 16 KB per consumer)
+    static constexpr int PLB = SR * 64 * 4;              // bytes of one plane's box
+    static constexpr int SSB = 4 * PLB;                  // bytes per super-slot (A, H, V, D)
+    static constexpr int THREADS = (NCW + 1) * 32;
+    static constexpr size_t SMEM = (size_t)NCW * NSS * SSB + (size_t)NCW * G::TILEB + NCW * NSS * 2 * sizeof(u64) + 128;
+    static_assert(G::UNR % SR == 0, "the row within a super-slot must be static in the unrolled body");
+};
+
+template <int HLEN>
+struct InvTmaParams {
+    CUtensorMap tm[4];                       // A, H, V, D as (nc, nr, batch) tensors, box (64, SR, 1)
+    float il[2][HLEN / 2], ih[2][HLEN / 2];  // [output parity][j]: IL / IH taps in accumulation order
+    float2 lh[2][HLEN / 2];                  // the same as (IL, IH) pairs for the row synthesis
+    const float* src[4];                     // A, H, V, D
+    size_t s_src[4];                         // plane strides (floats)
+    float* dst;
+    size_t s_dst;
+    int nr, nc, Mr, Mc;                      // coefficient and output plane sizes (Mr = 2 nr, Mc = 2 nc)
+    int TM;                                  // output row PAIRS per chunk
+    int ncb, ncg, nrc;                       // column blocks (strips), groups of NCW strips, row chunks
+    int pdl_early;
+    unsigned poll_ns;
+};
+
+template <int HLEN>
+__global__ void __launch_bounds__(InvTmaGeom<HLEN>::THREADS, HLEN <= 14 ? 3 : 2)
+    k_inv2d_tma(const __grid_constant__ InvTmaParams<HLEN> p)
+{
+    using T = InvTmaGeom<HLEN>;
+    using G = InvGeom<HLEN>;
+    constexpr int H2 = G::H2, NSLOT = G::NSLOT, WIN = G::WIN, SHIFT = G::SHIFT, UNR = G::UNR;
+    constexpr int NCW = T::NCW, SR = T::SR, NSS = T::NSS;
+    extern __shared__ unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
+    const int item = blockIdx.x;
+    const unsigned ring_s = (smem_u32(smem_raw) + 127u) & ~127u;      // tensor-map destinations are 128-byte aligned
+    unsigned char* const ring_g = smem_raw + (ring_s - smem_u32(smem_raw));
+    const unsigned tiles_off = NCW * NSS * T::SSB;
+    const unsigned bar_s = ring_s + tiles_off + NCW * (unsigned)G::TILEB;   // full[w][s] at +16*(w*NSS+s), empty behind it
+
+    const int cg = item % p.ncg, rest = item / p.ncg, rc = rest % p.nrc, plane = rest / p.nrc;
+    const int m0 = rc * p.TM;
+    const int nm = min(p.TM, p.nr - m0);
+    const int nrows = nm + WIN - 1;                 // coefficient rows this chunk consumes
+    const int nss = (nrows + SR - 1) / SR;
+    const int vr0 = m0 - G::CC;                     // first coefficient row (virtual: may be < 0 or run past nr)
+    const int nstrips = min(NCW, p.ncb - cg * NCW);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NCW * NSS * 2; i++) mbar_init(bar_s + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (p.pdl_early) pdl_launch_dependents();
+    pdl_wait();
+
+    if (warp == NCW) {
+        // ===================================================================================== producer warp
+        // the coefficients were written through the generic proxy (by the previous kernel of the stream): order the TMA
+        // engine's reads (async proxy) behind griddepcontrol.wait explicitly
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        auto issue = [&](const int k, const int w) {
+            const int slot = k % NSS;
+            const int row0v = vr0 + SR * k;
+            const int last_needed = min(row0v + SR, vr0 + nrows) - 1;
+            const bool rows_in = row0v >= 0 && last_needed < p.nr;
+            const unsigned full = bar_s + 16 * (w * NSS + slot);
+            const int xs = (cg * NCW + w) * G::WOUT - G::ALC;     // first coefficient column of the strip
+            const unsigned dst = ring_s + (w * NSS + slot) * T::SSB;
+            if (rows_in && xs >= 0 && xs + 64 <= p.nc) {
+                if (elect_one()) {
+                    mbar_expect_tx(full, T::SSB);
+#pragma unroll
+                    for (int a = 0; a < 4; a++) tma_load_3d(dst + a * T::PLB, &p.tm[a], xs, row0v, plane, full);
+                }
+            } else {
+                // periodic wrap in rows and / or columns: 8-byte pieces (xs and nc are even), wrapped index per piece
+                constexpr int PPR = 32;                    // pieces per row
+                constexpr int NIT = (4 * SR * PPR) / 32;   // pieces per lane
+#pragma unroll
+                for (int it = 0; it < NIT; it++) {
+                    const int i = lane + 32 * it;
+                    const int a = i / (SR * PPR), r = (i / PPR) % SR, c = i % PPR;
+                    int row = row0v + r;
+                    row += (row < 0) ? p.nr : 0;
+                    row -= (row >= p.nr) ? p.nr : 0;
+                    row = row < 0 ? 0 : (row >= p.nr ? p.nr - 1 : row);   // rows past the chunk's last are never used
+                    int x = xs + 2 * c;
+                    x += (x < 0) ? p.nc : 0;
+                    x -= (x >= p.nc) ? p.nc : 0;
+                    const float* g = p.src[a] + (size_t)plane * p.s_src[a] + (size_t)row * p.nc + x;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + a * T::PLB + r * 256 + c * 8), "l"(g) : "memory");
+                }
+                cp_async_mbar_arrive(full);   // +1 pending now, -1 when this lane's copies have landed
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full);
+            }
+            __syncwarp();
+        };
+        int next[NCW];
+#pragma unroll
+        for (int w = 0; w < NCW; w++) next[w] = 0;
+        int remaining = nstrips * nss;
+        while (remaining > 0) {
+            bool any = false;
+#pragma unroll
+            for (int w = 0; w < NCW; w++) {
+                const int k = next[w];
+                if (w < nstrips && k < nss) {
+                    unsigned ok = 1;
+                    if (k >= NSS) ok = mbar_poll(bar_s + 16 * (w * NSS + k % NSS) + 8, ((k / NSS) + 1) & 1);
+                    if (__shfl_sync(0xffffffffu, ok, 0)) {
+                        issue(k, w);
+                        next[w] = k + 1;
+                        remaining--;
+                        any = true;
+                    }
+                }
+            }
+            if (!any) __nanosleep(p.poll_ns);
+        }
+        return;
+    }
+
+    // ========================================================================================= consumer warps
+    if (warp >= nstrips) return;
+    const int cb = cg * NCW + warp;
+    const int k0 = cb * G::WOUT;
+    const unsigned my_bar = bar_s + 16 * warp * NSS;
+    unsigned char* const my_tile = ring_g + tiles_off + warp * G::TILEB;
+    // this lane's two columns inside a staged row of plane a: ring + slot * SSB + a * PLB + row * 256 + 8 * lane
+    unsigned lane_off = 8 * lane;
+    asm volatile("" : "+r"(lane_off));
+    const unsigned char* const my_ring = ring_g + warp * NSS * T::SSB + lane_off;
+
+    u64 wA[NSLOT], wH[NSLOT], wV[NSLOT], wD[NSLOT];  // register window, slot = (row index within the chunk) % NSLOT
+#pragma unroll
+    for (int i = 0; i < NSLOT; i++) wA[i] = wH[i] = wV[i] = wD[i] = 0ull;
+    unsigned soff = 0, bar = my_bar, parity = 0;     // ring position of the super-slot that holds the NEXT row to load
+    // row r of the chunk (r % SR == rin, static): ring -> window slot r % NSLOT
+    // A super-slot may only go back to the producer once its rows ARE in registers.  An arrive issued right behind the
+    // shared-memory loads does not wait for them (nothing has consumed their results yet), and the TMA refill -- async
+    // proxy, unordered against this warp's generic loads still in flight -- can overtake them: with three CTAs per SM
+    // about one super-slot in 10^4 then delivered rows of the NEXT refill (the forward kernel releases a slot after the
+    // arithmetic that consumed it, so it never saw this).  Here the arrive is (1) deferred until the first row of the
+    // next super-slot is loaded, one step later, and (2) made to DEPEND on every load of the slot it releases: one
+    // register of each goes into an XOR chain x and the barrier address is offset by (x * x) & 2 -- zero for every
+    // x, but not for ptxas (in PTX: LLVM knows that bit 1 of a square is clear and would drop the chain).
+    unsigned pbar = 0;   // "empty" barrier of the super-slot read last
+    auto release_prev = [&](const int r) {   // rows r - SR .. r - 1 (static window slots) made up that super-slot
+        unsigned x = 0;
+#pragma unroll
+        for (int q = 1; q <= SR; q++) {
+            const int sl = (r - q) % NSLOT;
+            x ^= (unsigned)wA[sl] ^ (unsigned)wH[sl];
+            x ^= (unsigned)wV[sl] ^ (unsigned)wD[sl];
+        }
+        __syncwarp();
+        if (lane == 0)
+            asm volatile(
+                "{\n"
+                ".reg .u32 t;\n"
+                "mul.lo.u32 t, %1, %1;\n"
+                "and.b32 t, t, 2;\n"
+                "add.u32 t, t, %0;\n"
+                "mbarrier.arrive.shared::cta.b64 _, [t];\n"
+                "}\n" ::"r"(pbar), "r"(x)
+                : "memory");
+    };
+    auto load_row = [&](const int r, const int rin) {
+        if (rin == 0) {
+            if (r >= SR) release_prev(r);
+            mbar_wait(bar, parity);
+        }
+        const float* c = reinterpret_cast<const float*>(my_ring + soff + rin * 256);
+        const float2 a = *reinterpret_cast<const float2*>(c);
+        const float2 h = *reinterpret_cast<const float2*>(c + T::PLB / 4);
+        const float2 v = *reinterpret_cast<const float2*>(c + 2 * (T::PLB / 4));
+        const float2 d = *reinterpret_cast<const float2*>(c + 3 * (T::PLB / 4));
+        wA[r % NSLOT] = pack2(a.x, a.y);
+        wH[r % NSLOT] = pack2(h.x, h.y);
+        wV[r % NSLOT] = pack2(v.x, v.y);
+        wD[r % NSLOT] = pack2(d.x, d.y);
+        if (rin == SR - 1) {   // on to the next super-slot; the last ones of a chunk are never refilled, nobody waits for them
+            pbar = bar + 8;
+            soff += T::SSB;
+            bar += 16;
+            if (soff == NSS * T::SSB) {
+                soff = 0;
+                bar = my_bar;
+                parity ^= 1;
+            }
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < WIN; i++) load_row(i, i % SR);
+
+    // ---- row synthesis side: lanes 0..LPR-1 take the even output row, lanes 16..16+LPR-1 the odd one
+    const int g = lane >> 4, lq = lane & 15;
+    const int px0 = 2 * k0 + 8 * lq;
+    const bool row_lane = lq < G::LPR;
+    float* out = p.dst + (size_t)plane * p.s_dst + (size_t)(2 * m0 + g) * p.Mc + px0;
+    const bool st0 = row_lane && px0 + 4 <= p.Mc, st1 = row_lane && px0 + 8 <= p.Mc;
+    unsigned tile_wr_off = 16 * ((lane >> 1) + (lane & 1) * G::ODD0), tile_rd_off = g * G::TROWB + 16 * lq;
+    asm volatile("" : "+r"(tile_wr_off), "+r"(tile_rd_off));
+    unsigned char* const tile_wr = my_tile + tile_wr_off;
+    const unsigned char* const tile_rd = my_tile + tile_rd_off;
+    ptrdiff_t out_step = 2 * (ptrdiff_t)p.Mc;
+    asm volatile("" : "+l"(out_step));
+
+    int s = 0;
+    bool more = true;
+    while (more) {
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {       // body: UNR output row pairs; register, ring-row and tile indices all static
+            if (s >= nm) {
+                more = false;
+                break;
+            }
+            if (s + 1 >= nm) pdl_launch_dependents();
+            if (s + 1 < nm) load_row(u + WIN, (u + WIN) % SR);   // the row that the NEXT pair adds to the window
+            const int sb = u % NSLOT, buf = u & 1;
+            // column synthesis, w_kern_inverse_pass1 (separable.cu:246-289): t1 = IL_y(A) + IH_y(H), t2 = IL_y(V) + IH_y(D)
+#pragma unroll
+            for (int par = 0; par < 2; par++) {
+                u64 sa = 0ull, sh = 0ull, sv = 0ull, sd = 0ull;
+#pragma unroll
+                for (int j = 0; j < H2; j++) {
+                    const int sl = (sb + (par ? SHIFT : 0) + j) % NSLOT;
+                    const u64 kl = pack2(p.il[par][j], p.il[par][j]), kh = pack2(p.ih[par][j], p.ih[par][j]);
+                    sa = ffma2(wA[sl], kl, sa);
+                    sh = ffma2(wH[sl], kh, sh);
+                    sv = ffma2(wV[sl], kl, sv);
+                    sd = ffma2(wD[sl], kh, sd);
+                }
+                float a0, a1, h0, h1, v0, v1, d0, d1;
+                unpack2(sa, a0, a1);
+                unpack2(sh, h0, h1);
+                unpack2(sv, v0, v1);
+                unpack2(sd, d0, d1);
+                *reinterpret_cast<float4*>(tile_wr + (buf * 2 + par) * G::TROWB) =
+                    make_float4(__fadd_rn(a0, h0), __fadd_rn(v0, d0), __fadd_rn(a1, h1), __fadd_rn(v1, d1));
+            }
+            __syncwarp();
+            // row synthesis, w_kern_inverse_pass2 (separable.cu:293-328): img = IL_x(t1) + IH_x(t2)
+            if (row_lane) {
+                u64 tw[G::NP];
+#pragma unroll
+                for (int v = 0; v < G::NP / 2; v++) {
+                    const float4 f = *reinterpret_cast<const float4*>(tile_rd + buf * 2 * G::TROWB +
+                                                                      16 * ((v >> 1) + (v & 1) * G::ODD0));
+                    tw[2 * v] = pack2(f.x, f.y);
+                    tw[2 * v + 1] = pack2(f.z, f.w);
+                }
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int e = k & 1;
+                    const int i0 = (k >> 1) + G::SHC + (e ? SHIFT : 0);
+                    u64 acc = 0ull;
+#pragma unroll
+                    for (int j = 0; j < H2; j++) acc = ffma2(tw[i0 + j], pack2(p.lh[e][j].x, p.lh[e][j].y), acc);
+                    float r1, r2;
+                    unpack2(acc, r1, r2);
+                    o[k] = __fadd_rn(r1, r2);
+                }
+                if (st0) *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+                if (st1) *reinterpret_cast<float4*>(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            out += out_step;
+            s++;
+        }
+    }
+}
+
 template <int HLEN>
 static bool inv_stream_eligible(const StreamLevelIO& io)
 {
@@ -1363,6 +1665,95 @@ static int pick_tm(int ncb, int nr, int batch, int per_sm)
     return TM;
 }
 
+// one level through the TMA-fed kernel; 1 = launched, 0 = shape not covered (16-byte-aligned rows needed), < 0 = error
+template <int HLEN>
+static int launch_inv_tma(const Taps& t, const StreamLevelIO& io, int batch, cudaStream_t s)
+{
+    using G = InvGeom<HLEN>;
+    using T = InvTmaGeom<HLEN>;
+    const int Mr = io.Nr, Mc = io.Nc, nr = Mr / 2, nc = Mc / 2;
+    if ((G::ALC & 3) != 0) return 0;   // a tensor-map box must start on a 16-byte boundary: hlen 12, 14, 16, 18
+    if (!inv_stream_eligible<HLEN>(io) || (nc & 3) || nr < T::SR) return 0;
+    const Plane2 src[4] = {io.A, io.H, io.V, io.D};
+    for (int a = 0; a < 4; a++)
+        if ((((uintptr_t)src[a].p) & 15) || (src[a].stride & 3)) return 0;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return 0;
+    static PerDeviceOnce once;
+    static int per_sm_dev[64];
+    int dev = 0;
+    {
+        const cudaError_t eo = once.run([&]() -> cudaError_t {
+            int d = 0, per_sm = 0;
+            cudaError_t e = cudaGetDevice(&d);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(k_inv2d_tma<HLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+            if (e != cudaSuccess) return e;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv2d_tma<HLEN>, T::THREADS, T::SMEM) != cudaSuccess || per_sm < 1) {
+                cudaGetLastError();
+                per_sm = 2;
+            }
+            per_sm_dev[d & 63] = per_sm;
+            return cudaSuccess;
+        }, &dev);
+        if (eo != cudaSuccess) return note_cuda(eo);
+    }
+    const int per_sm = per_sm_dev[dev & 63];
+    InvTmaParams<HLEN> p;
+    memset(&p, 0, sizeof p);
+    for (int a = 0; a < 4; a++) {
+        const cuuint64_t dims[3] = {(cuuint64_t)nc, (cuuint64_t)nr, (cuuint64_t)batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)nc * 4, (cuuint64_t)src[a].stride * 4};
+        const cuuint32_t box[3] = {64, (cuuint32_t)T::SR, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(&p.tm[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)src[a].p, dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 0;
+        p.src[a] = src[a].p;
+        p.s_src[a] = src[a].stride;
+    }
+    for (int par = 0; par < 2; par++) {
+        const int off = par ? G::SHIFT : 1 - G::SHIFT;
+        for (int j = 0; j < HLEN / 2; j++) {
+            p.il[par][j] = t.IL[HLEN - 1 - (2 * j + off)];
+            p.ih[par][j] = t.IH[HLEN - 1 - (2 * j + off)];
+            p.lh[par][j] = make_float2(p.il[par][j], p.ih[par][j]);
+        }
+    }
+    p.dst = io.img.p;
+    p.s_dst = io.img.stride;
+    p.nr = nr; p.nc = nc; p.Mr = Mr; p.Mc = Mc;
+    p.ncb = idiv_up(nc, G::WOUT);
+    p.ncg = idiv_up(p.ncb, T::NCW);
+    // chunk height: CTAs (NCW strips x TM row pairs, cost TM + 2.5) over sms x per_sm slots, as pick_tm
+    int TM = 32;
+    {
+        const long long slots = (long long)sm_count() * per_sm;
+        double best = 1e30;
+        for (int tm = 128; tm >= 4; tm -= 2) {
+            const long long items = (long long)p.ncg * idiv_up(nr, tm) * batch;
+            const double cost = (double)((items + slots - 1) / slots) * (tm + 2.5);
+            if (cost < best * 0.999) {
+                best = cost;
+                TM = tm;
+            }
+        }
+    }
+    if (const char* e = getenv("PDWT_TM")) TM = atoi(e) > 0 ? atoi(e) : TM;
+    p.TM = TM;
+    p.nrc = idiv_up(nr, TM);
+    p.pdl_early = pdl_mode() == 1;
+    static const unsigned poll_ns = []() { const char* e = getenv("PDWT_POLL_NS"); return e ? (unsigned)atoi(e) : 200u; }();
+    p.poll_ns = poll_ns;
+    const long long nctas = (long long)p.ncg * p.nrc * batch;
+    if (nctas > 0x7fffffff) return 0;
+    PDWT_PROF(prof_tag("k_inv2d_tma", Mr, Mc), s);
+    PDWT_CUDA(launch_pdl(k_inv2d_tma<HLEN>, dim3((unsigned)nctas), T::THREADS, T::SMEM, s, p));
+    PDWT_LAUNCH_CHECK();
+    return 1;
+}
+
 // Inverse levels io[0..nlev), coarsest first: io[l].A/H/V/D (Nr/2 x Nc/2) -> io[l].img (Nr x Nc); io[l+1].A must be
 // io[l].img.  Returns the number of LEADING levels launched (0 = the first level's shape is not covered), < 0 on error.
 template <int HLEN>
@@ -1373,6 +1764,10 @@ static int launch_inv_stream(const Taps& t, StreamPlans* plans, const StreamLeve
     while (n < nlev && n < kMaxLv && inv_stream_eligible<HLEN>(io[n])) n++;
     if (n == 0) return 0;
     if (!plans || !multi_level_on()) n = 1;   // see launch_fwd_stream
+    if (n == 1 && inv_tma_wanted((long long)io[0].Nr * io[0].Nc, batch)) {   // the TMA-fed variant of the same level kernel
+        const int done = launch_inv_tma<HLEN>(t, io[0], batch, s);
+        if (done != 0) return done;
+    }
     static PerDeviceOnce once;
     static int per_sm_dev[64];
     int dev = 0;

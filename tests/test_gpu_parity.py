@@ -115,6 +115,36 @@ def test_against_oracle(case, path):
     assert bitexact(W.get_image(), O.get_image())
 
 
+@pytest.mark.parametrize("shape,wname,levels,batch", [((512, 1024), "db7", 2, 1), ((256, 768), "sym8", 2, 3),
+                                                      ((384, 512), "db6", 1, 2), ((200, 520), "db9", 2, 1),
+                                                      ((1024, 1024), "db7", 3, 1)])
+def test_inverse_tma_variant_against_oracle(shape, wname, levels, batch, monkeypatch):
+    """k_inv2d_tma (producer warp + tensor-map ring; picked automatically for large batched launches) forced onto small
+    cases -- edge super-slots in rows and columns, strips cut by the plane, several chunks -- bit-exact against the
+    oracle and against the default level kernel (separable.cu:246-328)."""
+    x = rnd((batch,) + shape if batch > 1 else shape, 21)
+    rec = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PDWT_INV_TMA", mode)
+        W = Wavelets(x, wname, levels)
+        W.forward()
+        W.soft_threshold(3.0, 0, 1)
+        L = pdwt_b200.lib()
+        L.pdwt_profile_begin()
+        W.inverse()
+        ents = (pdwt_b200.ProfileEntry * 64)()
+        names = [ents[k].name.decode() for k in range(L.pdwt_profile_end(ents, 64))]
+        assert any(n.startswith("k_inv2d_tma") for n in names) == (mode == "1"), names   # the variant under test did run
+        rec[mode] = W.get_image()
+    assert bitexact(rec["1"], rec["0"])
+    for p in range(batch):
+        O = oracle.Wavelets(x[p] if batch > 1 else x, wname, levels)
+        O.forward()
+        O.soft_threshold(3.0, 0, 1)
+        O.inverse()
+        assert bitexact(rec["1"][p] if batch > 1 else rec["1"], O.get_image())
+
+
 def test_every_wavelet_roundtrips_and_matches_oracle():
     x = rnd((96, 160), 5)
     for wname in pdwt_b200.wavelet_names():
