@@ -1,5 +1,6 @@
 #!/bin/bash
-O=gpurun_out/exp64; mkdir -p $O
+# bit-exactness stress of the TMA-fed inverse level kernel against the default one, then bench.py with and without it
+O=gpurun_out/tma_inv_check; mkdir -p $O
 for cfg in "1 4096 94" "2 4096 46" "2 4096 64" "2 4096 128" "2 4096 94" "2 4096 32" "4 2048 94" "8 2048 94" "8 4096 0"; do set -- $cfg
   if [ "$3" = "0" ]; then B=$1 N=$2 REPS=6 python tools/tma_inv_stress.py 2>&1 | tail -1; else B=$1 N=$2 REPS=6 PDWT_TM=$3 python tools/tma_inv_stress.py 2>&1 | tail -1; fi
 done | tee $O/stress.txt
