@@ -583,6 +583,7 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
     // accumulator file with 14 MOVs per pair.
     oA -= (size_t)(H2 - 1) * nc_o; oH -= (size_t)(H2 - 1) * nc_o; oV -= (size_t)(H2 - 1) * nc_o; oD -= (size_t)(H2 - 1) * nc_o;
     int q = 0;                                    // row pair index within the chunk
+    unsigned touch = 0;                           // see the slot release below (short filters only)
     // one row pair whose two rows sit at `rowp` / `rowp + WW floats` of the ring
     auto pair_step = [&](const char* rowp) {
         float xa[G::NV * 4], xb[G::NV * 4];
@@ -613,6 +614,7 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
                 aHD[pp + 1][c] = ffma2(lohi1[c], kh, aHD[pp][c]);
             }
         }
+        if (H2 < SR / 2) touch ^= (unsigned)lohi0[0] ^ (unsigned)lohi0[NC - 1] ^ (unsigned)lohi1[0] ^ (unsigned)lohi1[NC - 1];
         TL(4, q == 0 && threadIdx.x == 0);
         // slot H2 received its last tap (j = hlen-1) in this pair
         if (col_ok && q >= H2 - 1) {
@@ -637,9 +639,27 @@ __global__ void __launch_bounds__(FwdGeom<HLEN>::THREADS, LOWOCC ? 2 : (HLEN <= 
         const char* ssp = lane_ring + soff;
 #pragma unroll
         for (int pin = 0; pin < SR / 2; pin++) pair_step(ssp + pin * (2 * G::WW * 4));
-        // every lane has consumed all rows of this super-slot: hand it back to the producer
+        // Every lane has consumed all rows of this super-slot: hand it back to the producer.  The release must not be
+        // ISSUED before the shared-memory loads of the slot have completed (the TMA refill is not ordered against generic
+        // loads in flight, see k_inv2d_tma); here every load feeds the row pass and the arrive sits behind that
+        // arithmetic in program order, and to keep it there whatever the scheduler does the barrier address is made to
+        // depend on accumulators that all SR/2 row pairs of the slot went into ((x * x) & 2 is 0 for every x).
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar + 8);
+        if (lane == 0) {
+            // slot min(SR/2, H2) took in the last min(SR/2, H2) pairs; with short filters (H2 < SR/2) the older pairs of
+            // the slot went into `touch` as they were computed
+            unsigned x = (unsigned)aLV[SR / 2 < H2 ? SR / 2 : H2][0] ^ (unsigned)aLV[SR / 2 < H2 ? SR / 2 : H2][NC - 1];
+            if (H2 < SR / 2) x ^= touch;
+            asm volatile(
+                "{\n"
+                ".reg .u32 t;\n"
+                "mul.lo.u32 t, %1, %1;\n"
+                "and.b32 t, t, 2;\n"
+                "add.u32 t, t, %0;\n"
+                "mbarrier.arrive.shared::cta.b64 _, [t];\n"
+                "}\n" ::"r"(bar + 8), "r"(x)
+                : "memory");
+        }
         soff += G::SSB;
         bar += 16;
         if (soff == NSS * G::SSB) {
