@@ -397,6 +397,16 @@ def run_ours(args):
                     roof[name] = {"avg_us": d[key], "frac": round(ab / (d[key] * 1e-6) / 1e9 / peak, 4),
                                   "how": f"{d['launches_each']} consecutive launches of this kernel alone between two CUDA "
                                          f"events, rotating buffers, {how}"}
+            # the second ceiling of this kernel (the separable DWT sits at the FP32 ridge): one level over R x C
+            # pixels does hlen FMAs per pixel in each of its two passes = 4 * hlen flop per pixel, on the CUDA cores
+            hlen = int(Ws[0].info.hlen)
+            fl = 4.0 * hlen * (ab / 8.0)
+            tf = fp32_peak_tflops()
+            roof["fp32"] = {"bound": "fp32 CUDA cores (no tensor cores: north_star)", "achieved": round(fl / (dur_us * 1e-6) / 1e12, 2),
+                            "peak": round(tf, 1), "unit": "TFLOP/s", "frac": round(fl / (dur_us * 1e-6) / 1e12 / tf, 4),
+                            "algorithmic_flops_per_launch": fl,
+                            "note": "the level kernels are co-limited by FP32 issue and HBM (DESIGN 3.4-3.6): packed FFMA2 is "
+                                    "about half of their instruction stream, ncu shows the FMA pipe 50-63 % busy"}
             tr = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the ncu capture
             if os.path.exists(tr) and args.workload == "c2":
                 roof["traffic"] = json.load(open(tr)).get(top.split("[")[0])
