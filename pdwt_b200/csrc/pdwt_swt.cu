@@ -205,6 +205,15 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
     // tile rows.  A task = one column x RPT consecutive tile rows, 4 sub-bands.
     const int xx = tid % K::TW;
     const int gx = gx0 + xx;
+    // output addressing hoisted out of the task loop: four plane pointers at this thread's column, one row step
+    // (the stores were 116 of the 271 instructions of a task when every one recomputed plane, row and column)
+    float* oA = A + (size_t)blockIdx.z * s_a + gx;
+    float* oH = H + (size_t)blockIdx.z * s_d + gx;
+    float* oV = V + (size_t)blockIdx.z * s_d + gx;
+    float* oD = D + (size_t)blockIdx.z * s_d + gx;
+    asm volatile("" : "+l"(oA), "+l"(oH), "+l"(oV), "+l"(oD));   // keep them: ptxas otherwise redoes blockIdx.z * stride per store
+    const size_t row_step = (size_t)f * Nc;
+    const bool col_in = gx < Nc;
     for (int m0 = (tid / K::TW) * K::RPT; m0 < K::TH; m0 += (kSwtThreads / K::TW) * K::RPT) {
         u64 ah[K::RPT], vd[K::RPT];   // (A, H) += lo * (L, H)[..],  (V, D) += hi * (L, H)[..]
 #pragma unroll
@@ -224,19 +233,20 @@ __global__ void __launch_bounds__(kSwtThreads, 2)
                 }
             }
         }
+        const int gy0 = ry + f * (mt * K::TH + m0);
+        size_t off = (size_t)gy0 * Nc;
 #pragma unroll
         for (int o = 0; o < K::RPT; o++) {
-            const int gy = ry + f * (mt * K::TH + m0 + o);
-            if (gy < Nr && gx < Nc) {
-                const size_t off = (size_t)gy * Nc + gx;
+            if (col_in && gy0 + o * f < Nr) {
                 float a, h, v, d;
                 sw_unpack2(ah[o], a, h);
                 sw_unpack2(vd[o], v, d);
-                A[(size_t)blockIdx.z * s_a + off] = a;
-                H[(size_t)blockIdx.z * s_d + off] = h;
-                V[(size_t)blockIdx.z * s_d + off] = v;
-                D[(size_t)blockIdx.z * s_d + off] = d;
+                oA[off] = a;
+                oH[off] = h;
+                oV[off] = v;
+                oD[off] = d;
             }
+            off += row_step;
         }
     }
 }
