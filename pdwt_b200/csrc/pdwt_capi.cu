@@ -450,14 +450,16 @@ int inv_sep_2d(const Ctx& x)
 
 // ---- (batched) 1-D: row passes only; A ping-pongs so that the last level lands in d_coeffs[0] ---------------
 // every level of a 1-D DWT from one launch (pdwt_rows_all.cu); false: run the per-level kernels
-bool rows_all(const Ctx& x, bool inverse, int* rc)
+bool rows_all(const Ctx& x, bool inverse, int* rc, bool swt = false)
 {
     const int L = x.w.nlevels;
     *rc = PDWT_OK;
     if (path_cap() < 1 || L < 2 || L > 32) return false;
     Plane2 bands[33];
     for (int l = 0; l <= L; l++) bands[l] = x.coeff(l);
-    const int done = inverse ? r_dwt1_inv_all(x.t, x.image(), bands, x.w.Nr, x.w.Nc, L, x.batch, x.s)
+    const int done = swt ? (inverse ? r_swt1_inv_all(x.t, x.image(), bands, x.w.Nr, x.w.Nc, L, x.batch, x.s)
+                                    : r_swt1_fwd_all(x.t, x.image(), bands, x.w.Nr, x.w.Nc, L, x.batch, x.s))
+                   : inverse ? r_dwt1_inv_all(x.t, x.image(), bands, x.w.Nr, x.w.Nc, L, x.batch, x.s)
                              : r_dwt1_fwd_all(x.t, x.image(), bands, x.w.Nr, x.w.Nc, L, x.batch, x.s);
     if (done < 0) *rc = done;
     return done != 0;
@@ -468,7 +470,7 @@ int fwd_sep_1d(const Ctx& x, bool swt)
     const int L = x.w.nlevels;
     int Nc = x.w.Nc;
     int rc_all;
-    if (!swt && rows_all(x, false, &rc_all)) return rc_all;
+    if (rows_all(x, false, &rc_all, swt)) return rc_all;
     Plane2 cur = x.image();
     for (int l = 0; l < L; l++) {
         Plane2 dstA = lands_in_c0(L, l) ? x.coeff(0) : x.scratch();
@@ -487,7 +489,7 @@ int inv_sep_1d(const Ctx& x, bool swt)
 {
     const int L = x.w.nlevels;
     int rc_all;
-    if (!swt && rows_all(x, true, &rc_all)) return rc_all;
+    if (rows_all(x, true, &rc_all, swt)) return rc_all;
     Plane2 cur = x.coeff(0);
     bool cur_is_c0 = true;
     for (int l = L - 1; l >= 0; l--) {

@@ -90,6 +90,10 @@ ORACLE_CASES = [
     # a dilation whose halo is wider than a short image allows (falls back), short filters
     ((300, 1100), "sym8", 4, 1, 1, 2), ((1000, 700), "db3", 3, 1, 1, 2), ((523, 1301), "db5", 4, 1, 1, 2),
     ((96, 2050), "haar", 4, 1, 1, 2), ((2049, 130), "coif2", 3, 1, 1, 2),
+    # batched 1-D SWT: all levels of a row in one launch (extended row buffers in shared memory); odd lengths, a long
+    # filter, a row too short for the coarsest dilation (falls back to the per-level kernels)
+    ((33, 1001), "sym8", 3, 1, 1, 1), ((5, 4096), "db4", 3, 1, 1, 1), ((4, 600), "db7", 4, 1, 1, 1),
+    ((3, 130), "db10", 3, 1, 1, 1), ((2, 12000), "db2", 5, 1, 1, 1),
 ]
 
 
