@@ -1,7 +1,7 @@
 #!/bin/bash
 # one gpurun call that produces everything profiles/ holds for a round: parity tests, smoke, both bench arms, the batched
 # workloads, the ncu launch list of the bench command and one ncu --set full capture of the six level kernels
-TAG=${1:-r02b}
+TAG=${1:-r02d}
 O=gpurun_out/$TAG; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader > $O/smi.txt 2>&1; nproc >> $O/smi.txt
 ( time python -m pytest tests -m gpu -x -q ) > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
